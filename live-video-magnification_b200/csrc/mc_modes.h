@@ -1,0 +1,105 @@
+// Per-mode device state + per-frame drivers: the B200 twins of magcore::MotionState / ColorState /
+// RieszState and magnifyMotion / magnifyColor / magnifyRiesz (reference
+// src/processing/magnification/MagnifyCore.hpp:24-40, :83-279).
+#pragma once
+#include <cufft.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/magcore_b200.h"
+#include "mc_internal.h"
+
+namespace mc {
+
+struct ModeCtx {
+    cudaStream_t stream;
+    const DeviceTables* tables;
+    uint64_t* launches;
+    std::string* err;
+    bool faithful0;
+    float* float_out;  // optional [lanes][h][w][C] pre-quantisation tap
+};
+
+struct StateRef {  // a named state plane set for mc_get_state / mc_set_state
+    float* ptr = nullptr;
+    int rows = 0, cols = 0, channels = 0, pitch = 0;
+    size_t plane_stride = 0;
+};
+
+// Simple owner of cudaMalloc'ed float buffers (freed together on reset()).
+struct DeviceArena {
+    std::vector<void*> blocks;
+    cudaError_t alloc(float** p, size_t floats);
+    cudaError_t alloc_bytes(void** p, size_t bytes);
+    void release();
+};
+
+struct MotionMode {
+    int lanes = 1;
+    bool empty = true;       // MotionState::empty()
+    bool allocated = false;
+    int levels = 0, channels = 0, w = 0, h = 0;
+    bool faithful = false;
+    std::vector<Level> lv;              // 0..levels
+    std::vector<float*> G, hi, lo, M;   // per level (null where not kept)
+    DeviceArena arena;
+
+    void reset();
+    mc_status process(const ModeCtx& ctx, const FrameIO& io, const mc_params& p, int levels, int* produced);
+    void find_state(const char* name, int level, StateRef& out);
+
+private:
+    mc_status allocate(const ModeCtx& ctx, const FrameIO& io, int levels);
+};
+
+struct ColorMode {
+    int lanes = 1;
+    bool allocated = false;
+    int levels = 0, channels = 0, w = 0, h = 0;
+    int cap = 0;            // ring capacity = getOptimalBufferSize(int(framerate))
+    int count = 0;          // frames currently in the window
+    int head = 0;           // physical slot of the OLDEST column
+    std::vector<Level> lv;  // gaussian chain levels 0..levels
+    std::vector<float*> G;  // pyrDown chain scratch (levels 1..levels-1) ; small level goes to the ring
+    std::vector<float*> U;  // up-chain scratch
+    std::vector<Level> ulv;
+    float* ring = nullptr;      // [planes][rowsP][cap] time-major rows: each pixel's samples contiguous
+    float* work = nullptr;      // gathered/filtered window [planes*rows][n]
+    cufftComplex* spec = nullptr;
+    float* minmax = nullptr;    // device scalars
+    float* filtered_small = nullptr;
+    int small_rows = 0;         // pixels of the small level
+    cufftHandle plan_r2c = 0, plan_c2r = 0;
+    int plan_n = 0;
+    DeviceArena arena;
+
+    void reset();
+    mc_status process(const ModeCtx& ctx, const FrameIO& io, const mc_params& p, int levels, int* produced);
+    void find_state(const char* name, int level, StateRef& out);
+};
+
+struct RieszMode {
+    int lanes = 1;
+    bool allocated = false;     // st.cur != null
+    int levels = 0, w = 0, h = 0;
+    double lo_freq = 0, hi_freq = 0, framerate = 0;   // itsFrequency / itsFramerate of the two filters
+    double loA[3] = {0, 0, 0}, loB[3] = {0, 0, 0}, hiA[3] = {0, 0, 0}, hiB[3] = {0, 0, 0};
+    std::vector<Level> lv;
+    DeviceArena arena;
+    // per level planes (lanes planes each)
+    std::vector<float*> cur_low, cur_rx, cur_ry, old_low, old_rx, old_ry;
+    std::vector<float*> oct;                       // octave (input of each level)
+    std::vector<float*> phase_c, phase_s;          // accumulated phase (shared by both filters: identical)
+    std::vector<float*> lo_r0c, lo_r0s, lo_r1c, lo_r1s, hi_r0c, hi_r0s, hi_r1c, hi_r1s;
+    std::vector<float*> amp, t_c, t_s;             // amplitude, (hi-lo)*A cos/sin
+    std::vector<float*> amp_blur, tb_c, tb_s, tmp0, tmp1, tmp2;
+    std::vector<float*> lab;                       // a,b planes + L
+    float *Lplane = nullptr, *Aplane = nullptr, *Bplane = nullptr, *collapse_a = nullptr, *collapse_b = nullptr;
+
+    void reset();
+    mc_status process(const ModeCtx& ctx, const FrameIO& io, const mc_params& p, int levels, int* produced);
+    void find_state(const char* name, int level, StateRef& out);
+};
+
+}  // namespace mc

@@ -1,0 +1,174 @@
+"""Motion (Laplace) parity: CUDA path (through the C ABI) vs the oracle, on a B200.
+
+Tolerances (SURVEY.md §A.7 / BASELINE.md §3): f32 output in [0,1] units before 8-bit quantisation
+max-abs < 1e-4; u8 output <= 1 LSB; state planes (Lab scale, L in [0,100]) max-abs < 1e-3 absolute
+and < 1e-5 relative to the plane's dynamic range."""
+import numpy as np
+import pytest
+
+import lvm_b200 as L
+from lvm_b200.synth import synth_frame
+from oracle import livim_oracle as O
+from common import make_cfgs, planar, u8_diff
+
+pytestmark = pytest.mark.gpu
+
+F32_TOL = 1e-4
+
+
+def run_pair(w, h, c, levels, n, chroma=0, faithful=True, amplification=20, check_state=True):
+    cfg, ocfg = make_cfgs(O.MODE_LAPLACE, amplification, 50.0, 0.4, 3.0, chroma, levels)
+    proc, oproc = L.MagnificationProcessor(0), O.MagnificationProcessor()
+    proc.set_option("faithful_level0", int(faithful))
+    proc.set_option("keep_float_output", 1)
+    worst_f, worst_u8 = 0.0, 0
+    for t in range(n):
+        f = synth_frame(t, w, h, c)
+        dbg = {}
+        produced, out = proc.process_image(f, cfg)
+        oprod, oout = oproc.process(f, ocfg, dbg)
+        assert produced and oprod
+        ref_f = dbg["output_bgr_f32"] if c == 3 else dbg["output_f32"]
+        got_f = proc.float_output(w, h, c)[0]
+        if c == 1:
+            got_f = got_f[..., 0]
+        worst_f = max(worst_f, float(np.abs(got_f - ref_f).max()))
+        worst_u8 = max(worst_u8, int(u8_diff(out, oout).max()))
+    lv_eff = min(max(levels, 1), L.calculateMaxLevels(w, h))
+    if check_state:
+        for name, ost in (("lowpassHi", oproc.motion.lowpassHi), ("lowpassLo", oproc.motion.lowpassLo)):
+            for lvl in range(lv_eff + 1):
+                got = proc.get_state(name, lvl)
+                if got is None:
+                    assert not faithful and lvl in (0, lv_eff)
+                    continue
+                ref = planar(ost[lvl])
+                d = float(np.abs(got[0] - ref).max())
+                rng = float(np.abs(ref).max()) + 1e-6
+                assert d < 1e-3 and d / rng < 2e-5, (name, lvl, d, rng)
+    return worst_f, worst_u8
+
+
+@pytest.mark.parametrize("w,h,c,levels", [
+    (320, 240, 3, 4), (320, 240, 1, 4), (240, 135, 3, 5), (135, 240, 1, 5), (67, 35, 3, 3), (30, 17, 1, 2),
+    (64, 64, 3, 1), (7, 9, 3, 4), (130, 66, 3, 9),
+])
+def test_free_running_small(w, h, c, levels):
+    wf, wu = run_pair(w, h, c, levels, 12, chroma=50)
+    assert wf < F32_TOL, wf
+    assert wu <= 1, wu
+
+
+def test_config1_640x480():
+    wf, wu = run_pair(640, 480, 3, 4, 32, chroma=0)
+    assert wf < F32_TOL and wu <= 1, (wf, wu)
+
+
+def test_config2_1080p_color_and_gray():
+    for c in (3, 1):
+        wf, wu = run_pair(1920, 1080, c, 6, 6, chroma=0)
+        assert wf < F32_TOL and wu <= 1, (c, wf, wu)
+
+
+def test_production_mode_matches_faithful():
+    """Skipping the dead level-0 / residual state (default) must not change the output."""
+    cfg, _ = make_cfgs(O.MODE_LAPLACE, 20, 50.0, 0.4, 3.0, 30, 5)
+    a, b = L.MagnificationProcessor(0), L.MagnificationProcessor(0)
+    a.set_option("faithful_level0", 1)
+    for t in range(8):
+        f = synth_frame(t, 322, 241, 3)
+        _, oa = a.process_image(f, cfg)
+        _, ob = b.process_image(f, cfg)
+        assert np.array_equal(oa, ob)
+    assert b.get_state("lowpassHi", 0) is None and b.get_state("lowpassHi", 1) is not None
+
+
+def test_teacher_forced_single_step():
+    """Inject the oracle's state for frame t-1, process frame t, compare output and new state."""
+    w, h, c, levels = 322, 241, 3, 5
+    cfg, ocfg = make_cfgs(O.MODE_LAPLACE, 20, 50.0, 0.4, 3.0, 40, levels)
+    proc, oproc = L.MagnificationProcessor(0), O.MagnificationProcessor()
+    proc.set_option("faithful_level0", 1)
+    proc.set_option("keep_float_output", 1)
+    for t in range(6):
+        f = synth_frame(t, w, h, c)
+        if t >= 1:
+            for lvl in range(levels + 1):
+                proc.set_state("lowpassHi", lvl, planar(oproc.motion.lowpassHi[lvl])[None])
+                proc.set_state("lowpassLo", lvl, planar(oproc.motion.lowpassLo[lvl])[None])
+        dbg = {}
+        _, out = proc.process_image(f, cfg)
+        _, oout = oproc.process(f, ocfg, dbg)
+        assert float(np.abs(proc.float_output(w, h, c)[0] - dbg["output_bgr_f32"]).max()) < F32_TOL
+        assert int(u8_diff(out, oout).max()) <= 1
+        for lvl in range(levels):
+            d = np.abs(proc.get_state("lowpassHi", lvl)[0] - planar(oproc.motion.lowpassHi[lvl])).max()
+            assert d < 1e-3, (t, lvl, d)
+
+
+def test_structural_reset_and_param_change():
+    """levels / size / channel changes reset state (MagnifyCore.hpp:53-65); alpha/cutoff changes do not."""
+    proc, oproc = L.MagnificationProcessor(0), O.MagnificationProcessor()
+    seq = [(320, 240, 3, 4, 20, 0.4, 3.0)] * 4 + [(320, 240, 3, 4, 35, 0.8, 2.0)] * 3 + \
+          [(320, 240, 3, 3, 35, 0.8, 2.0)] * 3 + [(200, 120, 1, 3, 35, 0.8, 2.0)] * 3
+    for t, (w, h, c, lv, amp, lo, hi) in enumerate(seq):
+        cfg, ocfg = make_cfgs(O.MODE_LAPLACE, amp, 50.0, lo, hi, 20, lv)
+        f = synth_frame(t, w, h, c)
+        produced, out = proc.process_image(f, cfg)
+        oprod, oout = oproc.process(f, ocfg)
+        assert produced == oprod and int(u8_diff(out, oout).max()) <= 1, t
+
+
+def test_passthrough_and_reset_semantics():
+    proc = L.MagnificationProcessor(0)
+    cfg, ocfg = make_cfgs(O.MODE_LAPLACE, 20, 50.0, 0.4, 3.0, 0, 4)
+    none_cfg = L.ProcessorConfig(magnification=L.MagnificationParams(mode=L.MagnificationMode.NONE))
+    f = synth_frame(0, 64, 48, 3)
+    fr = L.Frame(image=f, seq=7)
+    assert proc.process(fr, none_cfg) is fr                      # mode None -> same FrameRef
+    tiny = L.Frame(image=np.zeros((5, 40, 3), np.uint8))
+    assert proc.process(tiny, cfg) is tiny                        # too small -> identity
+    out = proc.process(fr, cfg)
+    assert out is not fr and out.seq == 7 and out.image is not f  # fresh buffer, metadata kept
+    # reset(): next frame behaves as the first frame again
+    oproc = O.MagnificationProcessor()
+    for t in range(3):
+        proc.process_image(synth_frame(t, 64, 48, 3), cfg)
+    proc.reset()
+    _, o1 = proc.process_image(synth_frame(9, 64, 48, 3), cfg)
+    _, r1 = oproc.process(synth_frame(9, 64, 48, 3), ocfg)
+    assert int(u8_diff(o1, r1).max()) <= 1
+
+
+def test_two_instances_and_lanes():
+    """Instances are independent; a 3-lane handle equals three 1-lane handles bit for bit."""
+    cfg, _ = make_cfgs(O.MODE_LAPLACE, 20, 50.0, 0.4, 3.0, 10, 4)
+    singles = [L.MagnificationProcessor(0) for _ in range(3)]
+    multi = L.MagnificationProcessor(0, lanes=3)
+    for t in range(5):
+        frames = [synth_frame(t, 160, 120, 3, seed=100 * k) for k in range(3)]
+        outs = [p.process_image(f, cfg)[1] for p, f in zip(singles, frames)]
+        _, mo = multi.process_image(np.stack(frames), cfg)
+        for k in range(3):
+            assert np.array_equal(mo[k], outs[k])
+
+
+def test_pipelined_submit_collect_matches_blocking():
+    import ctypes as C
+    cfg, _ = make_cfgs(O.MODE_LAPLACE, 20, 50.0, 0.4, 3.0, 0, 4)
+    a, b = L.MagnificationProcessor(0), L.MagnificationProcessor(0)
+    w, h, c, n = 320, 240, 3, 9
+    frames = [synth_frame(t, w, h, c) for t in range(n)]
+    ref = [a.process_image(f, cfg)[1] for f in frames]
+    outs = [np.empty_like(f) for f in frames]
+    depth, done = 3, 0
+    for t in range(n):
+        if t - done >= depth:
+            assert b.collect()
+            done += 1
+        b.submit(frames[t].ctypes.data, w, h, c, w * c, cfg, outs[t].ctypes.data, w * c)
+    while done < n:
+        assert b.collect()
+        done += 1
+    for t in range(n):
+        assert np.array_equal(outs[t], ref[t]), t

@@ -1,0 +1,138 @@
+"""CPU tests of the host side: C-ABI exports, parameter mapping, scalar design code, and the product's
+per-pixel __host__ __device__ functions compiled for the CPU (tests/hostcheck) against cv2."""
+import ctypes as C
+import os
+import re
+
+import cv2
+import numpy as np
+import pytest
+
+import lvm_b200 as L
+from lvm_b200 import capi
+from oracle import livim_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def hc(built):
+    lib = C.CDLL(built[1])
+    return lib
+
+
+def test_library_exports_every_declared_symbol(built):
+    hdr = open(os.path.join(ROOT, "include", "magcore_b200.h")).read()
+    declared = set(re.findall(r"\b(mc_[a-z_0-9]+)\s*\(", hdr))
+    declared -= {"mc_status", "mc_mode", "mc_params", "mc_handle"}
+    lib = C.CDLL(built[0])
+    missing = [s for s in sorted(declared) if not hasattr(lib, s)]
+    assert not missing, missing
+    assert declared == set(capi.SIGNATURES), declared ^ set(capi.SIGNATURES)
+    assert lib.mc_abi_version() == 1
+
+
+def test_no_cpu_fallback_without_gpu(built):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(L.MagcoreError) as e:
+        L.MagnificationProcessor(0)
+    assert e.value.status == capi.MC_ERR_NO_DEVICE
+
+
+def test_params_mapping_matches_reference_formulas(built):
+    for mode in (0, 1, 2):
+        for amp, wl, lo, hi, chroma, lv, fps in [(20, 50.0, 0.4, 3.0, 0, 6, 30.0), (50, 30.0, 1.0, 5.0, 25, 4, 25.0),
+                                                  (100, 80.0, 0.0, 1.2, 100, 3, 0.0), (10, 10.0, 14.9, 15.0, 7, 2, 30.0)]:
+            a = L.toParams(L.MagUiValues(L.MagnificationMode(mode), amp, wl, lo, hi, chroma, lv, fps))
+            b = O.to_params(mode, amp, wl, lo, hi, chroma, lv, fps)
+            for k in ("amplification", "coWavelength", "coLow", "coHigh", "chromAttenuation", "levels", "framerate"):
+                assert getattr(a, k) == getattr(b, k), (mode, k)
+
+
+def test_max_levels_and_buffer_size(built):
+    for w, h in [(1920, 1080), (640, 480), (3840, 2160), (6, 6), (5, 100), (7, 9), (130, 66), (1, 1), (4096, 6)]:
+        assert L.calculateMaxLevels(w, h) == O.calculate_max_levels(w, h)
+    assert (L.calculateMaxLevels(640, 480), L.calculateMaxLevels(1920, 1080), L.calculateMaxLevels(3840, 2160)) == (7, 8, 9)
+    for fps in (0, 1, 7, 8, 9, 24, 25, 30, 32, 33, 60, 120, 240):
+        assert L.getOptimalBufferSize(fps) == O.get_optimal_buffer_size(fps)
+
+
+def test_butterworth_matches_oracle_and_scipy(built):
+    from scipy.signal import butter
+    for wn in (0.4 / 15, 3.0 / 15, 0.8 / 15, 0.01, 0.5, 0.9):
+        a, b = L.butterworth(2, wn)
+        oa, ob = O.butterworth(2, wn)
+        sb, sa = butter(2, wn)
+        assert np.allclose(a, oa, rtol=0, atol=1e-13) and np.allclose(b, ob, rtol=0, atol=1e-13)
+        assert np.allclose(a, sa, rtol=0, atol=1e-13) and np.allclose(b, sb, rtol=0, atol=1e-13)
+    a, b = L.butterworth(4, 0.3)
+    sb, sa = butter(4, 0.3)
+    assert np.allclose(a, sa, atol=1e-12) and np.allclose(b, sb, atol=1e-12)
+
+
+def test_motion_gains_bit_identical(built):
+    lib = capi.lib()
+    for (w, h, lv, amp, wl) in [(1920, 1080, 6, 20, 50.0), (640, 480, 4, 20, 50.0), (3840, 2160, 8, 20, 50.0),
+                                (320, 240, 4, 35, 20.0), (100, 100, 3, 0, 0.0), (200, 100, 5, 150, 100.0)]:
+        p = capi.McParams()
+        lib.mc_params_from_ui(C.byref(p), 0, amp, wl, 0.4, 3.0, 0, lv, 30.0)
+        g = (C.c_float * (lv + 1))()
+        assert lib.mc_motion_gains(C.byref(p), lv, w, h, g) == 0
+        ref = O.motion_gains(O.to_params(0, amp, wl, 0.4, 3.0, 0, lv, 30.0), lv, w, h)
+        assert [np.float32(x) for x in g] == [np.float32(x) for x in ref]
+    # SURVEY §8d config 2 gains
+    ref = O.motion_gains(O.to_params(0, 20, 50.0, 0.4, 3.0, 0, 6, 30.0), 6, 1920, 1080)
+    assert np.allclose(ref, [0, -0.0725, 1.855, 5.710, 13.420, 20, 0], atol=2e-3)
+
+
+def test_bgr2lab_device_function_is_bit_exact_with_cv2(hc):
+    assert hc.hc_lut_entries() == 33 ** 3
+    rng = np.random.default_rng(0)
+    px = rng.integers(0, 256, (50000, 3), dtype=np.uint8)
+    edge = np.array([[0, 0, 0], [255, 255, 255], [255, 0, 0], [0, 255, 0], [0, 0, 255], [8, 8, 8], [7, 9, 247]], np.uint8)
+    px = np.concatenate([px, edge])
+    got = np.empty((len(px), 3), np.float32)
+    hc.hc_bgr_to_lab(px.ctypes.data_as(C.c_void_p), len(px), got.ctypes.data_as(C.c_void_p))
+    ref = cv2.cvtColor((px.astype(np.float32) * np.float32(1 / 255.0))[None], cv2.COLOR_BGR2Lab)[0]
+    assert np.array_equal(got, ref)
+
+
+def test_lab2bgr_device_function_matches_cv2(hc):
+    rng = np.random.default_rng(1)
+    px = rng.integers(0, 256, (40000, 3), dtype=np.uint8)
+    lab = cv2.cvtColor((px.astype(np.float32) * np.float32(1 / 255.0))[None], cv2.COLOR_BGR2Lab)[0]
+    lab = np.concatenate([lab, lab + rng.normal(0, 4, lab.shape).astype(np.float32),
+                          np.stack([rng.uniform(-10, 110, 5000), rng.uniform(-150, 150, 5000), rng.uniform(-150, 150, 5000)], -1).astype(np.float32)])
+    lab = np.ascontiguousarray(lab, np.float32)
+    got = np.empty_like(lab)
+    hc.hc_lab_to_bgr(lab.ctypes.data_as(C.c_void_p), len(lab), got.ctypes.data_as(C.c_void_p))
+    ref = cv2.cvtColor(lab[None], cv2.COLOR_Lab2BGR)[0]
+    assert float(np.abs(got - ref).max()) < 2e-5
+
+
+def test_u8_quantiser_and_ema_match_oracle_helpers(hc):
+    rng = np.random.default_rng(2)
+    x = np.concatenate([rng.uniform(-0.2, 1.2, 100000), np.arange(0, 256) / 255.0, (np.arange(0, 256) + 0.5) / 255.0,
+                        [np.nan, np.inf, -np.inf]]).astype(np.float32)
+    got = np.empty(len(x), np.uint8)
+    hc.hc_unit_to_u8(x.ctypes.data_as(C.c_void_p), len(x), got.ctypes.data_as(C.c_void_p))
+    with np.errstate(all="ignore"):
+        ref = O._f32_to_u8(x, 255.0, 1.0 / 255.0)
+    ok = np.isfinite(x)
+    assert np.array_equal(got[ok], ref[ok])
+    s = rng.normal(0, 30, 100000).astype(np.float32)
+    v = rng.normal(0, 30, 100000).astype(np.float32)
+    out = np.empty_like(s)
+    hc.hc_ema.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_void_p]
+    c = 0.4665119089088967
+    hc.hc_ema(s.ctypes.data, v.ctypes.data, len(s), c, out.ctypes.data)
+    ref = cv2.addWeighted(s, 1 - c, v, c, 0).ravel()
+    assert np.mean(out == ref) > 0.9999 and np.abs(out - ref).max() < 1e-5
+
+
+def test_gaussian_taps(hc):
+    t = np.empty(13, np.float32)
+    hc.hc_gauss13(t.ctypes.data_as(C.c_void_p))
+    assert np.array_equal(t, cv2.getGaussianKernel(13, 3.0, cv2.CV_32F).ravel())
