@@ -133,7 +133,9 @@ void* mc_stream(mc_handle* h);
  *   "faithful_level0" (default 0): also run the level-0 band + IIR state update that the reference
  *        performs although the gain loop multiplies that band by 0 (MagnifyCore.hpp:130-131); needed
  *        only to compare level-0 state planes with the oracle.
- *   "pipeline_depth"  (default 3) */
+ *   "pipeline_depth"  (default 3)
+ *   "keep_float_output" (default 0): keep the pre-quantisation float image (tests)
+ *   "profile_kernels" (default 0): see mc_profile_read */
 mc_status mc_set_option(mc_handle* h, const char* key, int value);
 
 /* Test-only access to temporal state planes as dense f32 [lanes][channels][rows][cols].
@@ -151,6 +153,11 @@ mc_status mc_get_float_output(mc_handle* h, float* dst, size_t dst_floats);
 
 /* Number of kernel launches this handle has issued (for bench.py's gpu_launches). */
 uint64_t mc_launch_count(mc_handle* h);
+
+/* Per-kernel device timing for bench.py's roofline: with option "profile_kernels" = 1 every launch
+ * is bracketed by CUDA events on the handle's stream.  mc_profile_read synchronises, drains them and
+ * writes text lines "kernel level launches total_ms\n" (NUL-terminated) into buf. */
+mc_status mc_profile_read(mc_handle* h, char* buf, size_t cap);
 
 /* Last error text for this handle (or for a failed mc_create when h == NULL); never NULL. */
 const char* mc_last_error(mc_handle* h);

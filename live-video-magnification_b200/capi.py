@@ -54,6 +54,7 @@ SIGNATURES = {
     "mc_set_state": (C.c_int, [_vp, C.c_char_p, C.c_int, _vp, C.c_size_t]),
     "mc_get_float_output": (C.c_int, [_vp, _vp, C.c_size_t]),
     "mc_launch_count": (C.c_uint64, [_vp]),
+    "mc_profile_read": (C.c_int, [_vp, C.c_char_p, C.c_size_t]),
     "mc_last_error": (C.c_char_p, [_vp]),
 }
 

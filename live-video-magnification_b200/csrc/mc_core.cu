@@ -45,7 +45,8 @@ struct mc_handle {
     float t_rx = 0.f, t_ry = 0.f, t_rw = 1.f, t_rh = 1.f;
 
     // options
-    bool faithful0 = false, keep_float = false;
+    bool faithful0 = false, keep_float = false, profile = false;
+    Profiler prof;
     int depth = 3;
 
     MotionMode motion;
@@ -181,7 +182,7 @@ mc_status process_device_impl(mc_handle* h, const uint8_t* d_in, int w, int hh, 
         fout = h->float_out;
     }
 
-    ModeCtx ctx{h->stream, &h->tables, &h->launches, &h->err, h->faithful0, fout};
+    ModeCtx ctx{h->stream, &h->tables, &h->launches, &h->err, h->faithful0, fout, h->profile ? &h->prof : nullptr};
     mc_status st = MC_OK;
     switch (p->mode) {
         case MC_MODE_LAPLACE: st = h->motion.process(ctx, io, *p, levels, produced); break;
@@ -355,6 +356,7 @@ mc_status mc_set_option(mc_handle* h, const char* key, int value) {
     if (!h || !key) return MC_ERR_INVALID;
     if (!std::strcmp(key, "faithful_level0")) { h->faithful0 = value != 0; return MC_OK; }
     if (!std::strcmp(key, "keep_float_output")) { h->keep_float = value != 0; return MC_OK; }
+    if (!std::strcmp(key, "profile_kernels")) { h->profile = value != 0; return MC_OK; }
     if (!std::strcmp(key, "pipeline_depth")) {
         if (value < 1 || value > 16 || !h->inflight.empty()) { h->err = "bad pipeline_depth"; return MC_ERR_INVALID; }
         h->depth = value;
@@ -530,4 +532,32 @@ extern "C" void* mc_host_alloc(size_t bytes) {
 }
 extern "C" void mc_host_free(void* p) {
     if (p) cudaFreeHost(p);
+}
+
+extern "C" mc_status mc_profile_read(mc_handle* h, char* buf, size_t cap) {
+    if (!h || !buf || cap == 0) return MC_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    struct Acc { std::string name; int level; int n; double ms; };
+    std::vector<Acc> acc;
+    for (auto& r : h->prof.recs) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, r.a, r.b);
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+        bool found = false;
+        for (auto& a : acc)
+            if (a.level == r.level && a.name == r.name) { a.n++; a.ms += ms; found = true; break; }
+        if (!found) acc.push_back(Acc{r.name, r.level, 1, ms});
+    }
+    h->prof.recs.clear();
+    std::string out;
+    char line[160];
+    for (auto& a : acc) {
+        std::snprintf(line, sizeof(line), "%s %d %d %.6f\n", a.name.c_str(), a.level, a.n, a.ms);
+        out += line;
+    }
+    if (out.size() + 1 > cap) { h->err = "profile buffer too small"; return MC_ERR_INVALID; }
+    std::memcpy(buf, out.c_str(), out.size() + 1);
+    return MC_OK;
 }

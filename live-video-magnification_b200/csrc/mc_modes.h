@@ -12,6 +12,20 @@
 
 namespace mc {
 
+// Optional per-launch event timing (bench roofline); events are drained by mc_profile_read.
+struct Profiler {
+    struct Rec { const char* name; int level; cudaEvent_t a, b; };
+    std::vector<Rec> recs;
+    bool begin(const char* name, int level, cudaStream_t s) {
+        Rec r{name, level, nullptr, nullptr};
+        if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return false;
+        cudaEventRecord(r.a, s);
+        recs.push_back(r);
+        return true;
+    }
+    void end(cudaStream_t s) { cudaEventRecord(recs.back().b, s); }
+};
+
 struct ModeCtx {
     cudaStream_t stream;
     const DeviceTables* tables;
@@ -19,7 +33,29 @@ struct ModeCtx {
     std::string* err;
     bool faithful0;
     float* float_out;  // optional [lanes][h][w][C] pre-quantisation tap
+    Profiler* prof;    // optional
 };
+
+// Launch bookkeeping shared by the mode drivers: counts the launch, optionally brackets it with events.
+#define MCK(call)                                                             \
+    do {                                                                      \
+        cudaError_t e__ = (call);                                             \
+        if (e__ != cudaSuccess) {                                             \
+            *ctx.err = std::string(#call) + ": " + cudaGetErrorString(e__);   \
+            return MC_ERR_CUDA;                                               \
+        }                                                                     \
+    } while (0)
+#define LAUNCH(name, level, call)                                             \
+    do {                                                                      \
+        const bool p__ = ctx.prof && ctx.prof->begin(name, level, ctx.stream);\
+        cudaError_t e__ = (call);                                             \
+        if (p__) ctx.prof->end(ctx.stream);                                   \
+        if (e__ != cudaSuccess) {                                             \
+            *ctx.err = std::string(name) + ": " + cudaGetErrorString(e__);    \
+            return MC_ERR_CUDA;                                               \
+        }                                                                     \
+        ++*ctx.launches;                                                      \
+    } while (0)
 
 struct StateRef {  // a named state plane set for mc_get_state / mc_set_state
     float* ptr = nullptr;

@@ -23,20 +23,6 @@ void DeviceArena::release() {
     blocks.clear();
 }
 
-#define MCK(call)                                                             \
-    do {                                                                      \
-        cudaError_t e__ = (call);                                             \
-        if (e__ != cudaSuccess) {                                             \
-            *ctx.err = std::string(#call) + ": " + cudaGetErrorString(e__);   \
-            return MC_ERR_CUDA;                                               \
-        }                                                                     \
-    } while (0)
-#define LAUNCH(call)      \
-    do {                  \
-        MCK(call);        \
-        ++*ctx.launches;  \
-    } while (0)
-
 void MotionMode::reset() {
     arena.release();
     lv.clear(); G.clear(); hi.clear(); lo.clear(); M.clear();
@@ -91,7 +77,7 @@ mc_status MotionMode::process(const ModeCtx& ctx, const FrameIO& io, const mc_pa
     // analysis: level 0 (u8 -> Lab/gray -> pyrDown)
     const int l_start = faithful ? 0 : 1;
     if (levels >= 2 || faithful)
-        LAUNCH(launch_ingest_down(io, *ctx.tables, lv[0], lv[1], G[1], faithful ? G[0] : nullptr, ctx.stream));
+        LAUNCH("ingest_down", 0, launch_ingest_down(io, *ctx.tables, lv[0], lv[1], G[1], faithful ? G[0] : nullptr, ctx.stream));
     // analysis: one fused kernel per level
     for (int l = l_start; l < levels; ++l) {
         LevelArgs a;
@@ -103,23 +89,23 @@ mc_status MotionMode::process(const ModeCtx& ctx, const FrameIO& io, const mc_pa
         a.first = first ? 1 : 0;
         a.c_hi = c_hi; a.one_minus_c_hi = 1 - c_hi; a.c_lo = c_lo; a.one_minus_c_lo = 1 - c_lo;
         a.gain = gains[(size_t)l];
-        LAUNCH(launch_level(a, ctx.stream));
+        LAUNCH("level", l, launch_level(a, ctx.stream));
     }
     if (first && faithful)  // st.lowpassHi/Lo[levels] = residual (MagnifyCore.hpp:100-101)
     {
         const size_t n = (size_t)planes * lv[(size_t)levels].plane;
-        LAUNCH(launch_copy_planes(hi[(size_t)levels], G[(size_t)levels], n, ctx.stream));
-        LAUNCH(launch_copy_planes(lo[(size_t)levels], G[(size_t)levels], n, ctx.stream));
+        LAUNCH("copy", levels, launch_copy_planes(hi[(size_t)levels], G[(size_t)levels], n, ctx.stream));
+        LAUNCH("copy", levels, launch_copy_planes(lo[(size_t)levels], G[(size_t)levels], n, ctx.stream));
     }
     const float* m1 = nullptr;
     if (!first && levels >= 2) {
         // synthesis: residual and finest band are zero (MagnifyCore.hpp:130-131), so the collapse
         // starts from band levels-1 and stops at level 1; level 0 is folded into egress.
         for (int l = levels - 2; l >= 1; --l)
-            LAUNCH(launch_collapse(lv[(size_t)l], lv[(size_t)l + 1], M[(size_t)l], M[(size_t)l + 1], planes, ctx.stream));
+            LAUNCH("collapse", l, launch_collapse(lv[(size_t)l], lv[(size_t)l + 1], M[(size_t)l], M[(size_t)l + 1], planes, ctx.stream));
         m1 = M[1];
     }
-    LAUNCH(launch_egress(io, *ctx.tables, lv[0], lv[levels >= 1 ? 1 : 0], m1, (float)p.chromAttenuation, ctx.float_out, ctx.stream));
+    LAUNCH("egress", 0, launch_egress(io, *ctx.tables, lv[0], lv[levels >= 1 ? 1 : 0], m1, (float)p.chromAttenuation, ctx.float_out, ctx.stream));
     empty = false;
     *produced = 1;
     return MC_OK;

@@ -226,6 +226,16 @@ class MagnificationProcessor(IProcessor):
     def launch_count(self) -> int:
         return int(self._lib.mc_launch_count(self._h))
 
+    def profile_read(self):
+        """-> {(kernel, level): (launches, total_ms)} since the last read (option profile_kernels=1)."""
+        buf = C.create_string_buffer(1 << 16)
+        self._check(self._lib.mc_profile_read(self._h, buf, len(buf)))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            k, lvl, n, ms = line.split()
+            out[(k, int(lvl))] = (int(n), float(ms))
+        return out
+
     # -- test-only state access --------------------------------------------------------------
     def state_dims(self, name: str, level: int = 0):
         r, c, ch = C.c_int(), C.c_int(), C.c_int()
