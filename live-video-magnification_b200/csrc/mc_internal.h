@@ -54,20 +54,26 @@ struct FrameIO {
     int w = 0, h = 0, channels = 0, lanes = 0;
 };
 
-// u8 frame -> (Lab | gray) -> pyrDown -> G1 planes.  Optionally materialises G0 planes (faithful mode).
-cudaError_t launch_ingest_down(const FrameIO& io, const DeviceTables& tb, const Level& l0, const Level& l1,
-                               float* g1, float* g0_or_null, cudaStream_t s);
+// u8 BGR frame -> Lab int16 planes [lanes*3][h][pitch16] (exact OpenCV LUT values)
+cudaError_t launch_lab16(const FrameIO& io, const DeviceTables& tb, int16_t* lab, int pitch16, size_t plane16,
+                         cudaStream_t s);
 
 struct LevelArgs {
+    int in_kind = 0;           // 0: f32 planes, 1: Lab int16 planes, 2: u8 gray frame
+    const void* g = nullptr;   // input planes of this level (fine)
+    size_t in_plane = 0;       // elements between planes
+    int in_row = 0;            // elements between rows
+    int channels = 1;
+    float sc[3] = {1, 1, 1}, of[3] = {0, 0, 0};   // value = fma(raw, sc[ch], of[ch]) for kinds 1, 2
     Level lf, lc;              // this level (fine) and the next (coarse)
-    const float* g;            // G_l planes (fine)
-    float* g_next;             // G_{l+1} planes (written)
-    float* hi; float* lo;      // state planes of this level
-    float* m;                  // gain * (hi - lo), may be null
-    int planes;
-    int first;                 // 1: hi = lo = band (MagnifyCore.hpp:98-103)
-    double c_hi, one_minus_c_hi, c_lo, one_minus_c_lo;
-    float gain;
+    float* g_next = nullptr;   // G_{l+1} planes (written)
+    float* hi = nullptr; float* lo = nullptr;     // state planes of this level
+    float* m = nullptr;        // gain * (hi - lo), may be null
+    int planes = 0;
+    int first = 0;             // 1: hi = lo = band (MagnifyCore.hpp:98-103)
+    int band = 1;              // 0: only pyrDown (the level-0 band never reaches the output)
+    double c_hi = 0, one_minus_c_hi = 0, c_lo = 0, one_minus_c_lo = 0;
+    float gain = 0;
 };
 // fused per level: pyrDown + pyrUp + subtract + dual-EMA update + gain (SpatialFilter.cpp:25-38,
 // TemporalFilter.cpp:9-22, MagnifyCore.hpp:127-134)
@@ -77,9 +83,11 @@ cudaError_t launch_level(const LevelArgs& a, cudaStream_t s);
 cudaError_t launch_collapse(const Level& lf, const Level& lc, float* m_fine, const float* m_coarse, int planes,
                             cudaStream_t s);
 
-// out = convert(input + chroma * pyrUp(cur_1)) (MagnifyCore.hpp:136-158).  m1 == nullptr: no motion.
-cudaError_t launch_egress(const FrameIO& io, const DeviceTables& tb, const Level& l0, const Level& l1,
-                          const float* m1, float chroma, float* float_out_or_null, cudaStream_t s);
+// out = convert(input + chroma * pyrUp(pyrUp(c2) + m1)) (MagnifyCore.hpp:136-158).
+// m1 == nullptr: no motion; c2 == nullptr: cur_1 = m1.  C == 3 reads `lab`, C == 1 reads io.in.
+cudaError_t launch_egress(const FrameIO& io, const DeviceTables& tb, const int16_t* lab, int pitch16, size_t plane16,
+                          const float* m1, const Level& l1, const float* c2, const Level& l2, float chroma,
+                          float* float_out_or_null, cudaStream_t s);
 
 // plane copy helpers
 cudaError_t launch_copy_planes(float* dst, const float* src, size_t n, cudaStream_t s);

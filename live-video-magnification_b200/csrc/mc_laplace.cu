@@ -1,12 +1,16 @@
-// Motion (Laplace) kernels for sm_100a: one fused kernel per pyramid level and direction.
+// Motion (Laplace) kernels for sm_100a.
 //
-//   ingest_down : u8 BGR/gray -> f32 (Lab via OpenCV's LUT) -> pyrDown            (MagnifyCore.hpp:87-93, SpatialFilter.cpp:31)
-//   level       : pyrDown + pyrUp + subtract + dual-EMA state update + gain        (SpatialFilter.cpp:25-38, TemporalFilter.cpp:9-22, MagnifyCore.hpp:127-134)
-//   collapse    : pyrUp + add                                                      (SpatialFilter.cpp:52-61)
-//   egress      : pyrUp + chroma attenuation + input+motion + Lab2BGR + u8         (MagnifyCore.hpp:136-158)
+//   lab16   : u8 BGR -> Lab (OpenCV LUT, exact) stored as int16 planes            (MagnifyCore.hpp:87-93)
+//   level   : pyrDown + pyrUp + subtract + dual-EMA state update + gain, fused    (SpatialFilter.cpp:25-38,
+//             per pyramid level; input f32 planes, Lab16 planes or u8 gray        TemporalFilter.cpp:9-22, MagnifyCore.hpp:127-134)
+//   collapse: pyrUp + add (small levels only)                                     (SpatialFilter.cpp:52-61)
+//   egress  : two pyrUp+add levels + chroma attenuation + input+motion +          (MagnifyCore.hpp:136-158)
+//             Lab2BGR + u8
 //
-// All are HBM-bandwidth-bound stencil / pointwise kernels (no tensor cores).  Tiles are staged in
-// shared memory; the row pass of each separable 5-tap filter runs out of that tile.
+// All are bandwidth-bound stencil / pointwise kernels (no tensor cores).  Each CTA stages one tile
+// (+halo) in shared memory with 128-bit loads, runs the separable 5-tap passes out of that tile, and
+// each thread owns a 4x2 pixel block so state planes move as 128-bit coalesced vectors.  Tiles that
+// touch an image border take a generic (slower) path that applies OpenCV's border rules.
 #include "mc_internal.h"
 
 namespace mc {
@@ -22,263 +26,406 @@ __device__ __forceinline__ float down5(float a, float b, float c, float d, float
 }
 
 // ------------------------------------------------------------------------------------------------
-// ingest_down: tile = 32x16 G1 pixels per CTA, all C channels (the Lab conversion is shared).
+// lab16: pointwise, 4 pixels per thread (12 input bytes = three 32-bit words).
 // ------------------------------------------------------------------------------------------------
-constexpr int ID_TW = 32, ID_TH = 16;
-constexpr int ID_SW = 2 * ID_TW + 3, ID_SH = 2 * ID_TH + 3;  // 67 x 35 source pixels
-constexpr int ID_SP = ID_SW + 1;                              // smem pitch 68
-
-template <int C>
-__global__ void __launch_bounds__(256) k_ingest_down(const uint8_t* __restrict__ in, size_t in_step,
-                                                     size_t in_lane_stride, int w0, int h0,
-                                                     const LabLutEntry* __restrict__ lut, float* __restrict__ g1,
-                                                     int w1, int h1, int pitch1, size_t plane1,
-                                                     float* __restrict__ g0, int pitch0, size_t plane0) {
-    __shared__ float s0[C][ID_SH][ID_SP];
-    __shared__ float sh[C][ID_SH][ID_TW];
+__global__ void __launch_bounds__(256) k_lab16(const uint8_t* __restrict__ in, size_t in_step, size_t in_lane_stride,
+                                               int w, int h, const LabLutEntry* __restrict__ lut,
+                                               int16_t* __restrict__ lab, int pitch16, size_t plane16, int aligned) {
     const int lane = blockIdx.z;
-    const int x1_0 = blockIdx.x * ID_TW, y1_0 = blockIdx.y * ID_TH;
-    const uint8_t* src = in + (size_t)lane * in_lane_stride;
-    const int gx0 = 2 * x1_0 - 2, gy0 = 2 * y1_0 - 2;
-
-    for (int idx = threadIdx.x; idx < ID_SH * ID_SW; idx += blockDim.x) {
-        const int r = idx / ID_SW, c = idx - r * ID_SW;
-        const int gy = reflect101(gy0 + r, h0), gx = reflect101(gx0 + c, w0);
-        const uint8_t* p = src + (size_t)gy * in_step + (size_t)gx * C;
-        if (C == 3) {
-            float L, A, B;
-            bgr_u8_to_lab(__ldg(p), __ldg(p + 1), __ldg(p + 2), lut, L, A, B);
-            s0[0][r][c] = L;
-            s0[C > 1 ? 1 : 0][r][c] = A;
-            s0[C > 2 ? 2 : 0][r][c] = B;
-            if (g0) {
-                // materialise G0 (faithful mode only): each in-image pixel is written by the tile
-                // whose interior covers it
-                const int ry = gy0 + r, rx = gx0 + c;
-                if (ry >= 2 * y1_0 && ry < 2 * (y1_0 + ID_TH) && ry < h0 && rx >= 2 * x1_0 &&
-                    rx < 2 * (x1_0 + ID_TW) && rx < w0) {
-                    float* q = g0 + (size_t)(lane * C) * plane0 + (size_t)ry * pitch0 + rx;
-                    q[0] = L; q[plane0] = A; q[2 * plane0] = B;
-                }
-            }
-        } else {
-            const float v = u8_to_unit(__ldg(p));
-            s0[0][r][c] = v;
-            if (g0) {
-                const int ry = gy0 + r, rx = gx0 + c;
-                if (ry >= 2 * y1_0 && ry < 2 * (y1_0 + ID_TH) && ry < h0 && rx >= 2 * x1_0 &&
-                    rx < 2 * (x1_0 + ID_TW) && rx < w0)
-                    g0[(size_t)lane * plane0 + (size_t)ry * pitch0 + rx] = v;
-            }
+    const int y = blockIdx.y;
+    const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (x >= w) return;
+    const uint8_t* p = in + (size_t)lane * in_lane_stride + (size_t)y * in_step + (size_t)x * 3;
+    uint8_t px[12];
+    if (aligned && x + 4 <= w) {
+        const uint32_t* q = reinterpret_cast<const uint32_t*>(p);
+        const uint32_t a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            px[i] = (a >> (8 * i)) & 0xff;
+            px[4 + i] = (b >> (8 * i)) & 0xff;
+            px[8 + i] = (c >> (8 * i)) & 0xff;
         }
-    }
-    __syncthreads();
-    // row pass
-    for (int idx = threadIdx.x; idx < ID_SH * ID_TW; idx += blockDim.x) {
-        const int r = idx / ID_TW, x = idx - r * ID_TW;
-        const int c = 2 * x + 2;
+    } else {
 #pragma unroll
-        for (int ch = 0; ch < C; ++ch)
-            sh[ch][r][x] = down5(s0[ch][r][c - 2], s0[ch][r][c - 1], s0[ch][r][c], s0[ch][r][c + 1], s0[ch][r][c + 2]);
+        for (int i = 0; i < 12; ++i) px[i] = (x + i / 3 < w) ? __ldg(p + i) : 0;
     }
-    __syncthreads();
-    // column pass + store
-    for (int idx = threadIdx.x; idx < ID_TH * ID_TW; idx += blockDim.x) {
-        const int y = idx / ID_TW, x = idx - y * ID_TW;
-        const int oy = y1_0 + y, ox = x1_0 + x;
-        if (oy < h1 && ox < w1) {
-            const int r = 2 * y + 2;
+    short L[4], A[4], B[4];
 #pragma unroll
-            for (int ch = 0; ch < C; ++ch) {
-                const float v = down5(sh[ch][r - 2][x], sh[ch][r - 1][x], sh[ch][r][x], sh[ch][r + 1][x], sh[ch][r + 2][x]) * kInv256;
-                g1[(size_t)(lane * C + ch) * plane1 + (size_t)oy * pitch1 + ox] = v;
+    for (int i = 0; i < 4; ++i) {
+        int sL, sA, sB;
+        bgr_u8_to_lab_fixed(px[3 * i], px[3 * i + 1], px[3 * i + 2], lut, sL, sA, sB);
+        L[i] = (short)sL; A[i] = (short)sA; B[i] = (short)sB;
+    }
+    int16_t* o = lab + (size_t)(lane * 3) * plane16 + (size_t)y * pitch16 + x;  // pitch16 % 64 == 0, x % 4 == 0
+    *reinterpret_cast<short4*>(o) = make_short4(L[0], L[1], L[2], L[3]);
+    *reinterpret_cast<short4*>(o + plane16) = make_short4(A[0], A[1], A[2], A[3]);
+    *reinterpret_cast<short4*>(o + 2 * plane16) = make_short4(B[0], B[1], B[2], B[3]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// level: tile = 64 x 32 fine pixels, 256 threads, thread block of 4 x 2 pixels.
+// ------------------------------------------------------------------------------------------------
+constexpr int TW = 64, TH = 32;
+constexpr int GW = TW + 8, GH = TH + 7;       // fine window 72 (71 used) x 39, origin (x0-4, y0-4)
+constexpr int DW = TW / 2 + 2, DH = TH / 2 + 2;  // coarse window 34 x 18, origin (x0/2-1, y0/2-1)
+constexpr int DP = 36;                        // coarse window pitch (8-byte aligned rows)
+
+enum { IN_F32 = 0, IN_LAB16 = 1, IN_U8 = 2 };
+
+template <int KIND>
+__device__ __forceinline__ float load_scalar(const void* base, size_t off, float sc, float of) {
+    if (KIND == IN_F32) return __ldg(reinterpret_cast<const float*>(base) + off);
+    if (KIND == IN_LAB16) return fmaf((float)__ldg(reinterpret_cast<const short*>(base) + off), sc, of);
+    return (float)__ldg(reinterpret_cast<const uint8_t*>(base) + off) * sc;
+}
+
+// Loads the fine window (GH x GW) of one plane into sG.  Interior tiles: 128-bit (or 64/32-bit for
+// narrow element types) vector loads; border tiles: scalar loads with BORDER_REFLECT_101.
+template <int KIND>
+__device__ __forceinline__ void load_fine_window(float (*sG)[GW], const void* base, int row_stride, int wf, int hf,
+                                                 int x0, int y0, bool interior, float sc, float of) {
+    if (interior) {
+        for (int i = threadIdx.x; i < GH * (GW / 4); i += 256) {
+            const int r = i / (GW / 4), c4 = i - r * (GW / 4);
+            const size_t off = (size_t)(y0 - 4 + r) * row_stride + (x0 - 4 + 4 * c4);
+            float4 v;
+            if (KIND == IN_F32) {
+                v = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + off));
+            } else if (KIND == IN_LAB16) {
+                const short4 s = __ldg(reinterpret_cast<const short4*>(reinterpret_cast<const short*>(base) + off));
+                v = make_float4(fmaf((float)s.x, sc, of), fmaf((float)s.y, sc, of), fmaf((float)s.z, sc, of), fmaf((float)s.w, sc, of));
+            } else {
+                const uchar4 s = __ldg(reinterpret_cast<const uchar4*>(reinterpret_cast<const uint8_t*>(base) + off));
+                v = make_float4((float)s.x * sc, (float)s.y * sc, (float)s.z * sc, (float)s.w * sc);
             }
+            *reinterpret_cast<float4*>(&sG[r][4 * c4]) = v;
+        }
+    } else {
+        for (int i = threadIdx.x; i < GH * GW; i += 256) {
+            const int r = i / GW, c = i - r * GW;
+            const int gy = reflect101(y0 - 4 + r, hf), gx = reflect101(x0 - 4 + c, wf);
+            sG[r][c] = load_scalar<KIND>(base, (size_t)gy * row_stride + gx, sc, of);
         }
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// level: tile = 64x16 fine pixels per CTA, one plane per blockIdx.z.
-// ------------------------------------------------------------------------------------------------
-constexpr int LV_TW = 64, LV_TH = 16;
-constexpr int LV_GW = LV_TW + 7, LV_GH = LV_TH + 7;   // fine window 71 x 23 (origin x0-4, y0-4)
-constexpr int LV_GP = LV_GW + 1;                      // 72
-constexpr int LV_DW = LV_TW / 2 + 2, LV_DH = LV_TH / 2 + 2;  // coarse window 34 x 10 (origin x0/2-1)
+struct LevelKArgs {
+    const void* g;            // input planes (f32 / int16 / u8)
+    size_t in_plane;          // elements between planes
+    int in_row;               // elements between rows
+    float sc[3], of[3];       // per-channel affine for int16 / u8 inputs
+    int channels;
+    Level lf, lc;
+    float* g_next;
+    float* hi; float* lo; float* m;
+    int first, band;
+    double c_hi, omc_hi, c_lo, omc_lo;
+    float gain;
+    int in_vec_ok;            // u8 rows are 4-byte aligned
+};
 
-__global__ void __launch_bounds__(256) k_level(LevelArgs a) {
-    __shared__ float sG[LV_GH][LV_GP];
-    __shared__ float sH[LV_GH][LV_DW];
-    __shared__ float sD[LV_DH][LV_DW];
-    __shared__ float sU[LV_DH][LV_TW];
+template <int KIND>
+__global__ void __launch_bounds__(256) k_level(const LevelKArgs a) {
+    __shared__ __align__(16) float sG[GH][GW];
+    __shared__ __align__(16) float sH[GH][DP];
+    __shared__ __align__(16) float sD[DH][DP];
     const int plane = blockIdx.z;
-    const int x0 = blockIdx.x * LV_TW, y0 = blockIdx.y * LV_TH;
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
     const int wf = a.lf.w, hf = a.lf.h, wc = a.lc.w, hc = a.lc.h;
-    const float* __restrict__ g = a.g + (size_t)plane * a.lf.plane;
+    const bool interior = x0 >= 4 && x0 + TW + 4 <= wf && y0 >= 4 && y0 + TH + 3 <= hf && (KIND != IN_U8 || a.in_vec_ok);
+    const int ch = plane % a.channels;
+    const void* base;
+    if (KIND == IN_F32) base = reinterpret_cast<const float*>(a.g) + (size_t)plane * a.in_plane;
+    else if (KIND == IN_LAB16) base = reinterpret_cast<const short*>(a.g) + (size_t)plane * a.in_plane;
+    else base = reinterpret_cast<const uint8_t*>(a.g) + (size_t)plane * a.in_plane;
+    load_fine_window<KIND>(sG, base, a.in_row, wf, hf, x0, y0, interior, a.sc[ch], a.of[ch]);
+    __syncthreads();
 
-    for (int idx = threadIdx.x; idx < LV_GH * LV_GW; idx += blockDim.x) {
-        const int r = idx / LV_GW, c = idx - r * LV_GW;
-        const int gy = reflect101(y0 - 4 + r, hf), gx = reflect101(x0 - 4 + c, wf);
-        sG[r][c] = __ldg(g + (size_t)gy * a.lf.pitch + gx);
+    // pyrDown row pass: sH[r][j] for the coarse columns of the window (pairs of columns per item)
+    if (interior) {
+        for (int i = threadIdx.x; i < GH * (DW / 2); i += 256) {
+            const int r = i / (DW / 2), jp = i - r * (DW / 2);
+            const float4 u = *reinterpret_cast<const float4*>(&sG[r][4 * jp]);
+            const float4 v = *reinterpret_cast<const float4*>(&sG[r][4 * jp + 4]);
+            float2 o;
+            o.x = down5(u.x, u.y, u.z, u.w, v.x);
+            o.y = down5(u.z, u.w, v.x, v.y, v.z);
+            *reinterpret_cast<float2*>(&sH[r][2 * jp]) = o;
+        }
+    } else {
+        for (int i = threadIdx.x; i < GH * DW; i += 256) {
+            const int r = i / DW, j = i - r * DW;
+            const int im = upsrc(x0 / 2 - 1 + j, wc);
+            int c = 2 * im - x0 + 4;
+            c = c < 2 ? 2 : (c > GW - 4 ? GW - 4 : c);
+            sH[r][j] = down5(sG[r][c - 2], sG[r][c - 1], sG[r][c], sG[r][c + 1], sG[r][c + 2]);
+        }
     }
     __syncthreads();
-    // pyrDown row pass at the (border-mapped) coarse columns of the window
-    for (int idx = threadIdx.x; idx < LV_GH * LV_DW; idx += blockDim.x) {
-        const int r = idx / LV_DW, j = idx - r * LV_DW;
-        const int im = upsrc(x0 / 2 - 1 + j, wc);
-        int c = 2 * im - x0 + 4;
-        c = c < 2 ? 2 : (c > LV_GW - 3 ? LV_GW - 3 : c);
-        sH[r][j] = down5(sG[r][c - 2], sG[r][c - 1], sG[r][c], sG[r][c + 1], sG[r][c + 2]);
-    }
-    __syncthreads();
-    // pyrDown column pass -> coarse window D (with pyrUp's border rule already applied), store G_{l+1}
+    // pyrDown column pass -> coarse window D (pyrUp's border rule pre-applied); store G_{l+1}
     float* __restrict__ gn = a.g_next + (size_t)plane * a.lc.plane;
-    for (int idx = threadIdx.x; idx < LV_DH * LV_DW; idx += blockDim.x) {
-        const int k = idx / LV_DW, j = idx - k * LV_DW;
-        const int iy = y0 / 2 - 1 + k, ix = x0 / 2 - 1 + j;
-        const int imy = upsrc(iy, hc);
-        int r = 2 * imy - y0 + 4;
-        r = r < 2 ? 2 : (r > LV_GH - 3 ? LV_GH - 3 : r);
-        const float v = down5(sH[r - 2][j], sH[r - 1][j], sH[r][j], sH[r + 1][j], sH[r + 2][j]) * kInv256;
-        sD[k][j] = v;
-        if (k >= 1 && k <= LV_TH / 2 && j >= 1 && j <= LV_TW / 2 && iy < hc && ix < wc)
-            gn[(size_t)iy * a.lc.pitch + ix] = v;
+    if (interior) {
+        for (int i = threadIdx.x; i < (DH / 2) * DW; i += 256) {
+            const int kp = i / DW, j = i - kp * DW;
+            const int r = 4 * kp;  // rows r..r+6 feed coarse rows 2kp, 2kp+1
+            const float f0 = sH[r][j], f1 = sH[r + 1][j], f2 = sH[r + 2][j], f3 = sH[r + 3][j], f4 = sH[r + 4][j],
+                        f5 = sH[r + 5][j], f6 = sH[r + 6][j];
+            const float d0 = down5(f0, f1, f2, f3, f4) * kInv256, d1 = down5(f2, f3, f4, f5, f6) * kInv256;
+            sD[2 * kp][j] = d0;
+            sD[2 * kp + 1][j] = d1;
+            if (j >= 1 && j <= TW / 2) {
+                const int ix = x0 / 2 - 1 + j;
+                const int iy = y0 / 2 - 1 + 2 * kp;
+                if (kp >= 1) gn[(size_t)iy * a.lc.pitch + ix] = d0;             // k = 2kp in [1,16] <=> kp >= 1
+                if (kp <= DH / 2 - 2) gn[(size_t)(iy + 1) * a.lc.pitch + ix] = d1;  // k = 2kp+1 <= 16
+            }
+        }
+    } else {
+        for (int i = threadIdx.x; i < DH * DW; i += 256) {
+            const int k = i / DW, j = i - k * DW;
+            const int iy = y0 / 2 - 1 + k, ix = x0 / 2 - 1 + j;
+            const int imy = upsrc(iy, hc);
+            int r = 2 * imy - y0 + 4;
+            r = r < 2 ? 2 : (r > GH - 3 ? GH - 3 : r);
+            const float v = down5(sH[r - 2][j], sH[r - 1][j], sH[r][j], sH[r + 1][j], sH[r + 2][j]) * kInv256;
+            sD[k][j] = v;
+            if (k >= 1 && k <= TH / 2 && j >= 1 && j <= TW / 2 && iy < hc && ix < wc) gn[(size_t)iy * a.lc.pitch + ix] = v;
+        }
     }
+    if (!a.band) return;
     __syncthreads();
-    // pyrUp row pass
-    for (int idx = threadIdx.x; idx < LV_DH * LV_TW; idx += blockDim.x) {
-        const int k = idx / LV_TW, x = idx - k * LV_TW;
-        const int j0 = (x >> 1) + 1;
-        sU[k][x] = (x & 1) ? (sD[k][j0] + sD[k][j0 + 1]) * 4.0f
-                           : (sD[k][j0 - 1] + sD[k][j0] * 6.0f + sD[k][j0 + 1]);
+
+    // pyrUp + band + temporal filter: thread (tx, ty) owns fine pixels x = 4tx..4tx+3, y = 2ty, 2ty+1
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    float up[2][4];
+    {
+        float e[3][4];  // pyrUp row pass for coarse rows ty, ty+1, ty+2 (window rows), fine cols 4tx..4tx+3
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            const float2 p0 = *reinterpret_cast<const float2*>(&sD[ty + q][2 * tx]);
+            const float2 p1 = *reinterpret_cast<const float2*>(&sD[ty + q][2 * tx + 2]);
+            e[q][0] = p0.x + p0.y * 6.0f + p1.x;
+            e[q][1] = (p0.y + p1.x) * 4.0f;
+            e[q][2] = p0.y + p1.x * 6.0f + p1.y;
+            e[q][3] = (p1.x + p1.y) * 4.0f;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            up[0][i] = (e[0][i] + e[1][i] * 6.0f + e[2][i]) * kInv64;
+            up[1][i] = ((e[1][i] + e[2][i]) * 4.0f) * kInv64;
+        }
     }
-    __syncthreads();
-    // pyrUp column pass, band, temporal filter
     float* __restrict__ hi = a.hi + (size_t)plane * a.lf.plane;
     float* __restrict__ lo = a.lo + (size_t)plane * a.lf.plane;
     float* __restrict__ m = a.m ? a.m + (size_t)plane * a.lf.plane : nullptr;
-    for (int idx = threadIdx.x; idx < LV_TH * LV_TW; idx += blockDim.x) {
-        const int y = idx / LV_TW, x = idx - y * LV_TW;
-        const int gy = y0 + y, gx = x0 + x;
+    const int gx = x0 + 4 * tx;
+#pragma unroll
+    for (int ry = 0; ry < 2; ++ry) {
+        const int gy = y0 + 2 * ty + ry;
         if (gy >= hf || gx >= wf) continue;
-        const int k0 = (y >> 1) + 1;
-        const float up = (y & 1) ? ((sU[k0][x] + sU[k0 + 1][x]) * 4.0f) * kInv64
-                                 : (sU[k0 - 1][x] + sU[k0][x] * 6.0f + sU[k0 + 1][x]) * kInv64;
-        const float band = sG[y + 4][x + 4] - up;
+        const float4 gv = *reinterpret_cast<const float4*>(&sG[2 * ty + ry + 4][4 * tx + 4]);
+        float band[4] = {gv.x - up[ry][0], gv.y - up[ry][1], gv.z - up[ry][2], gv.w - up[ry][3]};
         const size_t o = (size_t)gy * a.lf.pitch + gx;
+        // rows are padded to a multiple of 32 floats, so a full float4 at gx < wf is always in-bounds
         if (a.first) {
-            hi[o] = band;
-            lo[o] = band;
+            const float4 b4 = make_float4(band[0], band[1], band[2], band[3]);
+            *reinterpret_cast<float4*>(hi + o) = b4;
+            *reinterpret_cast<float4*>(lo + o) = b4;
         } else {
-            const float nh = ema(hi[o], band, a.one_minus_c_hi, a.c_hi);
-            const float nl = ema(lo[o], band, a.one_minus_c_lo, a.c_lo);
-            hi[o] = nh;
-            lo[o] = nl;
-            if (m) m[o] = (nh - nl) * a.gain;
+            const float4 h4 = *reinterpret_cast<const float4*>(hi + o);
+            const float4 l4 = *reinterpret_cast<const float4*>(lo + o);
+            float nh[4] = {h4.x, h4.y, h4.z, h4.w}, nl[4] = {l4.x, l4.y, l4.z, l4.w}, mm[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                nh[i] = ema(nh[i], band[i], a.omc_hi, a.c_hi);
+                nl[i] = ema(nl[i], band[i], a.omc_lo, a.c_lo);
+                mm[i] = (nh[i] - nl[i]) * a.gain;
+            }
+            *reinterpret_cast<float4*>(hi + o) = make_float4(nh[0], nh[1], nh[2], nh[3]);
+            *reinterpret_cast<float4*>(lo + o) = make_float4(nl[0], nl[1], nl[2], nl[3]);
+            if (m) *reinterpret_cast<float4*>(m + o) = make_float4(mm[0], mm[1], mm[2], mm[3]);
         }
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// collapse: cur_l = pyrUp(cur_{l+1}) + m_l  (in place in m_l)
+// collapse (small levels): cur_l = pyrUp(cur_{l+1}) + m_l, in place in m_l.  Tile 64 x 16.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void load_coarse_window(float (*sD)[LV_DW], const float* __restrict__ src, int pitch,
-                                                   int wc, int hc, int x0, int y0) {
-    for (int idx = threadIdx.x; idx < LV_DH * LV_DW; idx += blockDim.x) {
-        const int k = idx / LV_DW, j = idx - k * LV_DW;
-        const int iy = upsrc(y0 / 2 - 1 + k, hc), ix = upsrc(x0 / 2 - 1 + j, wc);
-        sD[k][j] = __ldg(src + (size_t)iy * pitch + ix);
-    }
-}
-
-__device__ __forceinline__ void up_rows(float (*sU)[LV_TW], const float (*sD)[LV_DW]) {
-    for (int idx = threadIdx.x; idx < LV_DH * LV_TW; idx += blockDim.x) {
-        const int k = idx / LV_TW, x = idx - k * LV_TW;
-        const int j0 = (x >> 1) + 1;
-        sU[k][x] = (x & 1) ? (sD[k][j0] + sD[k][j0 + 1]) * 4.0f
-                           : (sD[k][j0 - 1] + sD[k][j0] * 6.0f + sD[k][j0 + 1]);
-    }
-}
-
-__device__ __forceinline__ float up_col(const float (*sU)[LV_TW], int y, int x) {
-    const int k0 = (y >> 1) + 1;
-    return (y & 1) ? ((sU[k0][x] + sU[k0 + 1][x]) * 4.0f) * kInv64
-                   : (sU[k0 - 1][x] + sU[k0][x] * 6.0f + sU[k0 + 1][x]) * kInv64;
-}
+constexpr int CW = 64, CH_ = 16;
+constexpr int CDW = CW / 2 + 2, CDH = CH_ / 2 + 2;
 
 __global__ void __launch_bounds__(256) k_collapse(Level lf, Level lc, float* __restrict__ m_fine,
                                                   const float* __restrict__ m_coarse) {
-    __shared__ float sD[LV_DH][LV_DW];
-    __shared__ float sU[LV_DH][LV_TW];
+    __shared__ float sD[CDH][CDW];
+    __shared__ float sU[CDH][CW];
     const int plane = blockIdx.z;
-    const int x0 = blockIdx.x * LV_TW, y0 = blockIdx.y * LV_TH;
-    load_coarse_window(sD, m_coarse + (size_t)plane * lc.plane, lc.pitch, lc.w, lc.h, x0, y0);
+    const int x0 = blockIdx.x * CW, y0 = blockIdx.y * CH_;
+    const float* __restrict__ src = m_coarse + (size_t)plane * lc.plane;
+    for (int idx = threadIdx.x; idx < CDH * CDW; idx += blockDim.x) {
+        const int k = idx / CDW, j = idx - k * CDW;
+        const int iy = upsrc(y0 / 2 - 1 + k, lc.h), ix = upsrc(x0 / 2 - 1 + j, lc.w);
+        sD[k][j] = __ldg(src + (size_t)iy * lc.pitch + ix);
+    }
     __syncthreads();
-    up_rows(sU, sD);
+    for (int idx = threadIdx.x; idx < CDH * CW; idx += blockDim.x) {
+        const int k = idx / CW, x = idx - k * CW;
+        const int j0 = (x >> 1) + 1;
+        sU[k][x] = (x & 1) ? (sD[k][j0] + sD[k][j0 + 1]) * 4.0f : (sD[k][j0 - 1] + sD[k][j0] * 6.0f + sD[k][j0 + 1]);
+    }
     __syncthreads();
     float* __restrict__ mf = m_fine + (size_t)plane * lf.plane;
-    for (int idx = threadIdx.x; idx < LV_TH * LV_TW; idx += blockDim.x) {
-        const int y = idx / LV_TW, x = idx - y * LV_TW;
+    for (int idx = threadIdx.x; idx < CH_ * CW; idx += blockDim.x) {
+        const int y = idx / CW, x = idx - y * CW;
         const int gy = y0 + y, gx = x0 + x;
         if (gy >= lf.h || gx >= lf.w) continue;
+        const int k0 = (y >> 1) + 1;
+        const float up = (y & 1) ? ((sU[k0][x] + sU[k0 + 1][x]) * 4.0f) * kInv64
+                                 : (sU[k0 - 1][x] + sU[k0][x] * 6.0f + sU[k0 + 1][x]) * kInv64;
         const size_t o = (size_t)gy * lf.pitch + gx;
-        mf[o] = up_col(sU, y, x) + mf[o];
+        mf[o] = up + mf[o];
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// egress: tile = 64x16 output pixels, all channels.
+// egress: tile = 64 x 32 output pixels, all channels; thread block of 4 x 2 pixels.
+//   cur_1 = pyrUp(cur_2) + m_1 is rebuilt on the tile's level-1 window (34 x 18), then
+//   out = convert(input + chroma * pyrUp(cur_1)).
 // ------------------------------------------------------------------------------------------------
+constexpr int E2W = 20, E2H = 12;   // level-2 window, origin (x0/4-2, y0/4-2)
+constexpr int E2P = 20;
+
+struct EgressArgs {
+    const uint8_t* in; size_t in_step, in_lane_stride;      // gray input (C == 1)
+    const int16_t* lab; int pitch16; size_t plane16;        // Lab16 planes (C == 3)
+    uint8_t* out; size_t out_step, out_lane_stride;
+    int w0, h0;
+    const float4* gtab; LabInvCoeffs coeffs;
+    const float* m1; Level l1;      // band 1 (gain applied); null: no motion
+    const float* c2; Level l2;      // collapsed level 2; null: cur_1 = m_1
+    float chroma;
+    float* fout;
+};
+
 template <int C>
-__global__ void __launch_bounds__(256) k_egress(const uint8_t* __restrict__ in, size_t in_step, size_t in_lane_stride,
-                                                uint8_t* __restrict__ out, size_t out_step, size_t out_lane_stride,
-                                                int w0, int h0, const LabLutEntry* __restrict__ lut,
-                                                const float4* __restrict__ gtab, LabInvCoeffs coeffs,
-                                                const float* __restrict__ m1, Level l1, float chroma,
-                                                float* __restrict__ fout) {
-    __shared__ float sD[C][LV_DH][LV_DW];
-    __shared__ float sU[C][LV_DH][LV_TW];
+__global__ void __launch_bounds__(256) k_egress(const EgressArgs a) {
+    __shared__ __align__(16) float sC2[C][E2H][E2P];
+    __shared__ __align__(16) float sD[C][DH][DP];
     const int lane = blockIdx.z;
-    const int x0 = blockIdx.x * LV_TW, y0 = blockIdx.y * LV_TH;
-    if (m1) {
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+    const int w1 = a.l1.w, h1 = a.l1.h;
+    if (a.m1) {
+        if (a.c2) {
+            for (int i = threadIdx.x; i < C * E2H * E2W; i += 256) {
+                const int ch = i / (E2H * E2W), rem = i - ch * (E2H * E2W);
+                const int k = rem / E2W, j = rem - k * E2W;
+                const int iy = upsrc(y0 / 4 - 2 + k, a.l2.h), ix = upsrc(x0 / 4 - 2 + j, a.l2.w);
+                sC2[ch][k][j] = __ldg(a.c2 + (size_t)(lane * C + ch) * a.l2.plane + (size_t)iy * a.l2.pitch + ix);
+            }
+            __syncthreads();
+        }
+        // level-1 window: position (k, j) <-> level-1 pixel upsrc(y0/2-1+k), upsrc(x0/2-1+j)
+        for (int i = threadIdx.x; i < C * DH * DW; i += 256) {
+            const int ch = i / (DH * DW), rem = i - ch * (DH * DW);
+            const int k = rem / DW, j = rem - k * DW;
+            const int y1 = upsrc(y0 / 2 - 1 + k, h1), x1 = upsrc(x0 / 2 - 1 + j, w1);
+            float v = __ldg(a.m1 + (size_t)(lane * C + ch) * a.l1.plane + (size_t)y1 * a.l1.pitch + x1);
+            if (a.c2) {
+                // pyrUp of level 2 at (y1, x1): window index of level-2 pixel i is i - (x0/4 - 2); the
+                // border rule was applied when the window was loaded (entries hold s[upsrc(i)]).
+                const int jx = (x1 >> 1) - (x0 / 4 - 2), ky = (y1 >> 1) - (y0 / 4 - 2);
+                float r[3];
 #pragma unroll
-        for (int ch = 0; ch < C; ++ch)
-            load_coarse_window(sD[ch], m1 + (size_t)(lane * C + ch) * l1.plane, l1.pitch, l1.w, l1.h, x0, y0);
-        __syncthreads();
-#pragma unroll
-        for (int ch = 0; ch < C; ++ch) up_rows(sU[ch], sD[ch]);
+                for (int q = 0; q < 3; ++q) {
+                    const float* row = sC2[ch][ky - 1 + q];
+                    r[q] = (x1 & 1) ? (row[jx] + row[jx + 1]) * 4.0f : (row[jx - 1] + row[jx] * 6.0f + row[jx + 1]);
+                }
+                const float up = (y1 & 1) ? ((r[1] + r[2]) * 4.0f) * kInv64 : (r[0] + r[1] * 6.0f + r[2]) * kInv64;
+                v = up + v;
+            }
+            sD[ch][k][j] = v;
+        }
         __syncthreads();
     }
-    const uint8_t* src = in + (size_t)lane * in_lane_stride;
-    uint8_t* dst = out + (size_t)lane * out_lane_stride;
-    for (int idx = threadIdx.x; idx < LV_TH * LV_TW; idx += blockDim.x) {
-        const int y = idx / LV_TW, x = idx - y * LV_TW;
-        const int gy = y0 + y, gx = x0 + x;
-        if (gy >= h0 || gx >= w0) continue;
-        const uint8_t* p = src + (size_t)gy * in_step + (size_t)gx * C;
-        uint8_t* q = dst + (size_t)gy * out_step + (size_t)gx * C;
-        if (C == 3) {
-            float L, A, B;
-            bgr_u8_to_lab(__ldg(p), __ldg(p + 1), __ldg(p + 2), lut, L, A, B);
-            if (m1) {
-                // motion planes a,b *= chromAttenuation, then output = input + motion (MagnifyCore.hpp:140-148)
-                L = L + up_col(sU[0], y, x);
-                A = A + up_col(sU[C > 1 ? 1 : 0], y, x) * chroma;
-                B = B + up_col(sU[C > 2 ? 2 : 0], y, x) * chroma;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int gx = x0 + 4 * tx;
+    if (gx >= a.w0) return;
+    float up[C][2][4];
+    if (a.m1) {
+#pragma unroll
+        for (int ch = 0; ch < C; ++ch) {
+            float e[3][4];
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                const float2 p0 = *reinterpret_cast<const float2*>(&sD[ch][ty + q][2 * tx]);
+                const float2 p1 = *reinterpret_cast<const float2*>(&sD[ch][ty + q][2 * tx + 2]);
+                e[q][0] = p0.x + p0.y * 6.0f + p1.x;
+                e[q][1] = (p0.y + p1.x) * 4.0f;
+                e[q][2] = p0.y + p1.x * 6.0f + p1.y;
+                e[q][3] = (p1.x + p1.y) * 4.0f;
             }
-            float ob, og, orr;
-            lab_to_bgr(L, A, B, coeffs, gtab, ob, og, orr);
-            q[0] = unit_to_u8(ob);
-            q[1] = unit_to_u8(og);
-            q[2] = unit_to_u8(orr);
-            if (fout) {
-                float* f = fout + (((size_t)lane * h0 + gy) * w0 + gx) * 3;
-                f[0] = ob; f[1] = og; f[2] = orr;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                up[ch][0][i] = (e[0][i] + e[1][i] * 6.0f + e[2][i]) * kInv64;
+                up[ch][1][i] = ((e[1][i] + e[2][i]) * 4.0f) * kInv64;
+            }
+        }
+    }
+#pragma unroll
+    for (int ry = 0; ry < 2; ++ry) {
+        const int gy = y0 + 2 * ty + ry;
+        if (gy >= a.h0) continue;
+        uint8_t o8[4 * C];
+        float of[4 * C];
+        if (C == 3) {
+            const int16_t* lp = a.lab + (size_t)(lane * 3) * a.plane16 + (size_t)gy * a.pitch16 + gx;
+            const short4 sL = __ldg(reinterpret_cast<const short4*>(lp));
+            const short4 sA = __ldg(reinterpret_cast<const short4*>(lp + a.plane16));
+            const short4 sB = __ldg(reinterpret_cast<const short4*>(lp + 2 * a.plane16));
+            const short vL[4] = {sL.x, sL.y, sL.z, sL.w}, vA[4] = {sA.x, sA.y, sA.z, sA.w}, vB[4] = {sB.x, sB.y, sB.z, sB.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float L = (float)vL[i] * (100.0f / 16384.0f);
+                float A = fmaf((float)vA[i], 1.0f / 64.0f, -128.0f);
+                float B = fmaf((float)vB[i], 1.0f / 64.0f, -128.0f);
+                if (a.m1) {
+                    // a,b motion planes *= chromAttenuation, then output = input + motion (MagnifyCore.hpp:140-148)
+                    L = L + up[0][ry][i];
+                    A = A + up[C > 1 ? 1 : 0][ry][i] * a.chroma;
+                    B = B + up[C > 2 ? 2 : 0][ry][i] * a.chroma;
+                }
+                float ob, og, orr;
+                lab_to_bgr(L, A, B, a.coeffs, a.gtab, ob, og, orr);
+                of[3 * i] = ob; of[3 * i + 1] = og; of[3 * i + 2] = orr;
+                o8[3 * i] = unit_to_u8(ob); o8[3 * i + 1] = unit_to_u8(og); o8[3 * i + 2] = unit_to_u8(orr);
             }
         } else {
-            float v = u8_to_unit(__ldg(p));
-            if (m1) v = v + up_col(sU[0], y, x);
-            q[0] = unit_to_u8(v);
-            if (fout) fout[((size_t)lane * h0 + gy) * w0 + gx] = v;
+            const uint8_t* p = a.in + (size_t)lane * a.in_lane_stride + (size_t)gy * a.in_step + gx;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float v = (gx + i < a.w0) ? u8_to_unit(__ldg(p + i)) : 0.0f;
+                if (a.m1) v = v + up[0][ry][i];
+                of[i] = v;
+                o8[i] = unit_to_u8(v);
+            }
+        }
+        uint8_t* q = a.out + (size_t)lane * a.out_lane_stride + (size_t)gy * a.out_step + (size_t)gx * C;
+        const bool full = gx + 4 <= a.w0;
+        if (full && ((reinterpret_cast<uintptr_t>(q) & 3) == 0)) {
+#pragma unroll
+            for (int wd = 0; wd < C; ++wd)
+                reinterpret_cast<uint32_t*>(q)[wd] = (uint32_t)o8[4 * wd] | ((uint32_t)o8[4 * wd + 1] << 8) |
+                                                     ((uint32_t)o8[4 * wd + 2] << 16) | ((uint32_t)o8[4 * wd + 3] << 24);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4 * C; ++i)
+                if (gx + i / C < a.w0) q[i] = o8[i];
+        }
+        if (a.fout) {
+            float* f = a.fout + (((size_t)lane * a.h0 + gy) * a.w0 + gx) * C;
+#pragma unroll
+            for (int i = 0; i < 4 * C; ++i)
+                if (gx + i / C < a.w0) f[i] = of[i];
         }
     }
 }
@@ -292,40 +439,50 @@ inline unsigned cdiv(int a, int b) { return (unsigned)((a + b - 1) / b); }
 
 }  // namespace
 
-cudaError_t launch_ingest_down(const FrameIO& io, const DeviceTables& tb, const Level& l0, const Level& l1,
-                               float* g1, float* g0, cudaStream_t s) {
-    dim3 grid(cdiv(l1.w, ID_TW), cdiv(l1.h, ID_TH), io.lanes);
-    if (io.channels == 3)
-        k_ingest_down<3><<<grid, 256, 0, s>>>(io.in, io.in_step, io.in_lane_stride, l0.w, l0.h, tb.lab_lut, g1, l1.w,
-                                              l1.h, l1.pitch, l1.plane, g0, l0.pitch, l0.plane);
-    else
-        k_ingest_down<1><<<grid, 256, 0, s>>>(io.in, io.in_step, io.in_lane_stride, l0.w, l0.h, tb.lab_lut, g1, l1.w,
-                                              l1.h, l1.pitch, l1.plane, g0, l0.pitch, l0.plane);
+cudaError_t launch_lab16(const FrameIO& io, const DeviceTables& tb, int16_t* lab, int pitch16, size_t plane16,
+                         cudaStream_t s) {
+    const int aligned = (reinterpret_cast<uintptr_t>(io.in) % 4 == 0) && (io.in_step % 4 == 0) && (io.in_lane_stride % 4 == 0);
+    dim3 grid(cdiv(cdiv(io.w, 4), 256), io.h, io.lanes);
+    k_lab16<<<grid, 256, 0, s>>>(io.in, io.in_step, io.in_lane_stride, io.w, io.h, tb.lab_lut, lab, pitch16, plane16, aligned);
     return cudaGetLastError();
 }
 
 cudaError_t launch_level(const LevelArgs& a, cudaStream_t s) {
-    dim3 grid(cdiv(a.lf.w, LV_TW), cdiv(a.lf.h, LV_TH), a.planes);
-    k_level<<<grid, 256, 0, s>>>(a);
+    LevelKArgs k;
+    k.g = a.g; k.in_plane = a.in_plane; k.in_row = a.in_row; k.channels = a.channels;
+    for (int i = 0; i < 3; ++i) { k.sc[i] = a.sc[i]; k.of[i] = a.of[i]; }
+    k.lf = a.lf; k.lc = a.lc; k.g_next = a.g_next; k.hi = a.hi; k.lo = a.lo; k.m = a.m;
+    k.first = a.first; k.band = a.band;
+    k.c_hi = a.c_hi; k.omc_hi = a.one_minus_c_hi; k.c_lo = a.c_lo; k.omc_lo = a.one_minus_c_lo;
+    k.gain = a.gain;
+    k.in_vec_ok = a.in_kind == IN_U8 ? ((reinterpret_cast<uintptr_t>(a.g) % 4 == 0) && (a.in_row % 4 == 0) && (a.in_plane % 4 == 0)) : 1;
+    dim3 grid(cdiv(a.lf.w, TW), cdiv(a.lf.h, TH), a.planes);
+    if (a.in_kind == IN_F32) k_level<IN_F32><<<grid, 256, 0, s>>>(k);
+    else if (a.in_kind == IN_LAB16) k_level<IN_LAB16><<<grid, 256, 0, s>>>(k);
+    else k_level<IN_U8><<<grid, 256, 0, s>>>(k);
     return cudaGetLastError();
 }
 
 cudaError_t launch_collapse(const Level& lf, const Level& lc, float* m_fine, const float* m_coarse, int planes,
                             cudaStream_t s) {
-    dim3 grid(cdiv(lf.w, LV_TW), cdiv(lf.h, LV_TH), planes);
+    dim3 grid(cdiv(lf.w, CW), cdiv(lf.h, CH_), planes);
     k_collapse<<<grid, 256, 0, s>>>(lf, lc, m_fine, m_coarse);
     return cudaGetLastError();
 }
 
-cudaError_t launch_egress(const FrameIO& io, const DeviceTables& tb, const Level& l0, const Level& l1,
-                          const float* m1, float chroma, float* fout, cudaStream_t s) {
-    dim3 grid(cdiv(l0.w, LV_TW), cdiv(l0.h, LV_TH), io.lanes);
-    if (io.channels == 3)
-        k_egress<3><<<grid, 256, 0, s>>>(io.in, io.in_step, io.in_lane_stride, io.out, io.out_step, io.out_lane_stride,
-                                         l0.w, l0.h, tb.lab_lut, tb.inv_gamma, tb.inv_coeffs, m1, l1, chroma, fout);
-    else
-        k_egress<1><<<grid, 256, 0, s>>>(io.in, io.in_step, io.in_lane_stride, io.out, io.out_step, io.out_lane_stride,
-                                         l0.w, l0.h, tb.lab_lut, tb.inv_gamma, tb.inv_coeffs, m1, l1, chroma, fout);
+cudaError_t launch_egress(const FrameIO& io, const DeviceTables& tb, const int16_t* lab, int pitch16, size_t plane16,
+                          const float* m1, const Level& l1, const float* c2, const Level& l2, float chroma,
+                          float* fout, cudaStream_t s) {
+    EgressArgs a;
+    a.in = io.in; a.in_step = io.in_step; a.in_lane_stride = io.in_lane_stride;
+    a.lab = lab; a.pitch16 = pitch16; a.plane16 = plane16;
+    a.out = io.out; a.out_step = io.out_step; a.out_lane_stride = io.out_lane_stride;
+    a.w0 = io.w; a.h0 = io.h;
+    a.gtab = tb.inv_gamma; a.coeffs = tb.inv_coeffs;
+    a.m1 = m1; a.l1 = l1; a.c2 = c2; a.l2 = l2; a.chroma = chroma; a.fout = fout;
+    dim3 grid(cdiv(io.w, TW), cdiv(io.h, TH), io.lanes);
+    if (io.channels == 3) k_egress<3><<<grid, 256, 0, s>>>(a);
+    else k_egress<1><<<grid, 256, 0, s>>>(a);
     return cudaGetLastError();
 }
 

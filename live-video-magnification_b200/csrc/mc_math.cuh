@@ -59,9 +59,9 @@ MC_HD uint8_t scaled_to_u8(float x, float a, float b) {
 
 // cv::cvtColor(COLOR_BGR2Lab) on CV_32F input that came from u8/255 — bit-exact restatement of
 // OpenCV's 33^3 int16 LUT + 4-bit fixed-point trilinear interpolation.
-// lut is [b][g][r] packed entries.  Output Lab: L in [0,100], a,b in [-128,128).
-MC_HD void bgr_u8_to_lab(uint8_t b8, uint8_t g8, uint8_t r8, const LabLutEntry* __restrict__ lut,
-                         float& L, float& A, float& B) {
+// lut is [b][g][r] packed entries.  Fixed-point result: L*2^14/100, (a+128)*64, (b+128)*64.
+MC_HD void bgr_u8_to_lab_fixed(uint8_t b8, uint8_t g8, uint8_t r8, const LabLutEntry* __restrict__ lut,
+                               int& sL, int& sA, int& sB) {
 #if defined(__CUDA_ARCH__)
     const int cb = __float2int_rn(u8_to_unit(b8) * 16384.0f);
     const int cg = __float2int_rn(u8_to_unit(g8) * 16384.0f);
@@ -74,7 +74,7 @@ MC_HD void bgr_u8_to_lab(uint8_t b8, uint8_t g8, uint8_t r8, const LabLutEntry* 
     const int tb = cb >> 9, tg = cg >> 9, tr = cr >> 9;
     const int xb = (cb >> 5) & 15, xg = (cg >> 5) & 15, xr = (cr >> 5) & 15;
     const int tb1 = tb + 1 > 32 ? 32 : tb + 1, tg1 = tg + 1 > 32 ? 32 : tg + 1;
-    int sL = 0, sA = 0, sB = 0;
+    sL = 0; sA = 0; sB = 0;
 #pragma unroll
     for (int db = 0; db < 2; ++db) {
 #pragma unroll
@@ -98,6 +98,13 @@ MC_HD void bgr_u8_to_lab(uint8_t b8, uint8_t g8, uint8_t r8, const LabLutEntry* 
     sL = (sL + 2048) >> 12;
     sA = (sA + 2048) >> 12;
     sB = (sB + 2048) >> 12;
+}
+
+// Float Lab as OpenCV returns it: L in [0,100], a,b in [-128,128).
+MC_HD void bgr_u8_to_lab(uint8_t b8, uint8_t g8, uint8_t r8, const LabLutEntry* __restrict__ lut,
+                         float& L, float& A, float& B) {
+    int sL, sA, sB;
+    bgr_u8_to_lab_fixed(b8, g8, r8, lut, sL, sA, sB);
     L = (float)sL * (100.0f / 16384.0f);
     A = fmaf((float)sA, 1.0f / 64.0f, -128.0f);
     B = fmaf((float)sB, 1.0f / 64.0f, -128.0f);
@@ -124,19 +131,21 @@ MC_HD float spline_gamma(float v, const float4* __restrict__ tab) {
 // output clipped to [0,1]); restated from OpenCV's Lab2RGBfloat, checked against cv2 to ~1e-5.
 MC_HD void lab_to_bgr(float L, float a, float b, const LabInvCoeffs& k, const float4* __restrict__ gtab,
                       float& ob, float& og, float& orr) {
+    // constant divisions are written as reciprocal multiplies (<= 1 ulp from the divide; the parity
+    // budget is 1e-4) — IEEE divides would triple the instruction count of the egress kernel
     float Y, fy;
     if (L <= 8.0f) {
-        Y = L / 903.3f;
+        Y = L * (1.0f / 903.3f);
         fy = 7.787f * Y + 16.0f / 116.0f;
     } else {
-        fy = (L + 16.0f) / 116.0f;
+        fy = (L + 16.0f) * (1.0f / 116.0f);
         Y = fy * fy * fy;
     }
-    float fx = a / 500.0f + fy;
-    float fz = fy - b / 200.0f;
+    float fx = a * (1.0f / 500.0f) + fy;
+    float fz = fy - b * (1.0f / 200.0f);
     const float fth = 6.0f / 29.0f;
-    const float X = fx <= fth ? (fx - 16.0f / 116.0f) / 7.787f : fx * fx * fx;
-    const float Z = fz <= fth ? (fz - 16.0f / 116.0f) / 7.787f : fz * fz * fz;
+    const float X = fx <= fth ? (fx - 16.0f / 116.0f) * (1.0f / 7.787f) : fx * fx * fx;
+    const float Z = fz <= fth ? (fz - 16.0f / 116.0f) * (1.0f / 7.787f) : fz * fz * fz;
     float vb = k.c[0] * X + k.c[1] * Y + k.c[2] * Z;
     float vg = k.c[3] * X + k.c[4] * Y + k.c[5] * Z;
     float vr = k.c[6] * X + k.c[7] * Y + k.c[8] * Z;

@@ -79,6 +79,9 @@ struct MotionMode {
     bool faithful = false;
     std::vector<Level> lv;              // 0..levels
     std::vector<float*> G, hi, lo, M;   // per level (null where not kept)
+    int16_t* lab16 = nullptr;           // Lab planes of the current frame (C == 3)
+    int pitch16 = 0;
+    size_t plane16 = 0;
     DeviceArena arena;
 
     void reset();

@@ -26,6 +26,7 @@ void DeviceArena::release() {
 void MotionMode::reset() {
     arena.release();
     lv.clear(); G.clear(); hi.clear(); lo.clear(); M.clear();
+    lab16 = nullptr;
     allocated = false;
     empty = true;
 }
@@ -50,12 +51,19 @@ mc_status MotionMode::allocate(const ModeCtx& ctx, const FrameIO& io, int nlevel
         const size_t n = planes * lv[(size_t)l].plane;
         const bool band_level = l < levels;                       // bands 0..levels-1, residual = levels
         const bool live = band_level && l >= 1;                   // bands whose gain can be non-zero
-        if (l >= 1 || faithful) MCK(arena.alloc(&G[(size_t)l], n));
+        if (l >= 1) MCK(arena.alloc(&G[(size_t)l], n));
         if (live || faithful) {
             MCK(arena.alloc(&hi[(size_t)l], n));
             MCK(arena.alloc(&lo[(size_t)l], n));
         }
         if (live) MCK(arena.alloc(&M[(size_t)l], n));
+    }
+    if (channels == 3) {
+        pitch16 = round_up(w, 64);
+        plane16 = (size_t)h * pitch16;
+        void* p = nullptr;
+        MCK(arena.alloc_bytes(&p, planes * plane16 * sizeof(int16_t)));
+        lab16 = (int16_t*)p;
     }
     allocated = true;
     return MC_OK;
@@ -74,19 +82,33 @@ mc_status MotionMode::process(const ModeCtx& ctx, const FrameIO& io, const mc_pa
     double c_lo = p.coLow, c_hi = p.coHigh;
     if (c_lo == 0) c_lo = 0.01;  // TemporalFilter.cpp:11-12
 
-    // analysis: level 0 (u8 -> Lab/gray -> pyrDown)
-    const int l_start = faithful ? 0 : 1;
-    if (levels >= 2 || faithful)
-        LAUNCH("ingest_down", 0, launch_ingest_down(io, *ctx.tables, lv[0], lv[1], G[1], faithful ? G[0] : nullptr, ctx.stream));
-    // analysis: one fused kernel per level
-    for (int l = l_start; l < levels; ++l) {
+    // ingest: u8 BGR -> Lab16 planes (gray frames are read directly by the level-0 kernel)
+    if (channels == 3) LAUNCH("lab16", 0, launch_lab16(io, *ctx.tables, lab16, pitch16, plane16, ctx.stream));
+
+    // analysis: one fused kernel per level (level 0 only builds G1 unless the faithful option is on)
+    const int l_begin = (levels >= 2 || faithful) ? 0 : levels;
+    for (int l = l_begin; l < levels; ++l) {
         LevelArgs a;
+        if (l == 0) {
+            if (channels == 3) {
+                a.in_kind = 1; a.g = lab16; a.in_plane = plane16; a.in_row = pitch16;
+                a.sc[0] = 100.0f / 16384.0f; a.of[0] = 0.0f;
+                a.sc[1] = a.sc[2] = 1.0f / 64.0f; a.of[1] = a.of[2] = -128.0f;
+            } else {
+                a.in_kind = 2; a.g = io.in; a.in_plane = io.in_lane_stride; a.in_row = (int)io.in_step;
+                a.sc[0] = 0.003921568859368563f;
+            }
+        } else {
+            a.in_kind = 0; a.g = G[(size_t)l]; a.in_plane = lv[(size_t)l].plane; a.in_row = lv[(size_t)l].pitch;
+        }
+        a.channels = channels;
         a.lf = lv[(size_t)l]; a.lc = lv[(size_t)l + 1];
-        a.g = G[(size_t)l]; a.g_next = G[(size_t)l + 1];
+        a.g_next = G[(size_t)l + 1];
         a.hi = hi[(size_t)l]; a.lo = lo[(size_t)l];
         a.m = first ? nullptr : M[(size_t)l];
         a.planes = planes;
         a.first = first ? 1 : 0;
+        a.band = (l >= 1 || faithful) ? 1 : 0;
         a.c_hi = c_hi; a.one_minus_c_hi = 1 - c_hi; a.c_lo = c_lo; a.one_minus_c_lo = 1 - c_lo;
         a.gain = gains[(size_t)l];
         LAUNCH("level", l, launch_level(a, ctx.stream));
@@ -98,14 +120,18 @@ mc_status MotionMode::process(const ModeCtx& ctx, const FrameIO& io, const mc_pa
         LAUNCH("copy", levels, launch_copy_planes(lo[(size_t)levels], G[(size_t)levels], n, ctx.stream));
     }
     const float* m1 = nullptr;
+    const float* c2 = nullptr;
     if (!first && levels >= 2) {
         // synthesis: residual and finest band are zero (MagnifyCore.hpp:130-131), so the collapse
-        // starts from band levels-1 and stops at level 1; level 0 is folded into egress.
-        for (int l = levels - 2; l >= 1; --l)
+        // starts from band levels-1; levels 1 and 0 are folded into egress.
+        for (int l = levels - 2; l >= 2; --l)
             LAUNCH("collapse", l, launch_collapse(lv[(size_t)l], lv[(size_t)l + 1], M[(size_t)l], M[(size_t)l + 1], planes, ctx.stream));
         m1 = M[1];
+        if (levels >= 3) c2 = M[2];
     }
-    LAUNCH("egress", 0, launch_egress(io, *ctx.tables, lv[0], lv[levels >= 1 ? 1 : 0], m1, (float)p.chromAttenuation, ctx.float_out, ctx.stream));
+    const Level& l1 = lv[levels >= 1 ? 1 : 0];
+    const Level& l2 = lv[levels >= 2 ? 2 : 0];
+    LAUNCH("egress", 0, launch_egress(io, *ctx.tables, lab16, pitch16, plane16, m1, l1, c2, l2, (float)p.chromAttenuation, ctx.float_out, ctx.stream));
     empty = false;
     *produced = 1;
     return MC_OK;
