@@ -1,11 +1,442 @@
-// Color mode — placeholder until the Gaussian + ideal-FFT path lands.
+// Color mode — device twin of magcore::magnifyColor (reference
+// src/processing/magnification/MagnifyCore.hpp:163-206): Gaussian pyrDown chain, rolling temporal
+// window kept as a device ring buffer, ideal band-pass along time with cuFFT (R2C -> CCS-mask
+// multiply -> C2R), global min-max normalisation, pyrUp chain (+ bilinear resize), min-max stretch.
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+
 #include "mc_modes.h"
+
 namespace mc {
-void ColorMode::reset() { arena.release(); allocated = false; count = 0; head = 0; }
-mc_status ColorMode::process(const ModeCtx& ctx, const FrameIO&, const mc_params&, int, int* produced) {
-    *produced = 0;
-    *ctx.err = "Color mode not implemented yet";
-    return MC_ERR_UNSUPPORTED;
+
+namespace {
+
+// monotonic float <-> uint encoding so atomicMin/atomicMax order like floats
+__device__ __forceinline__ unsigned f2ord(float f) {
+    const unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
+__device__ __forceinline__ float ord2f(unsigned u) {
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+__global__ void k_mm_init(unsigned* mm, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) mm[i] = (i & 1) ? 0u : 0xffffffffu;  // even: min slot, odd: max slot
+}
+
+// u8 interleaved frame -> f32 planes [lanes*C][h][pitch], value = (float)u8  (MagnifyCore.hpp:168-169)
+template <int C>
+__global__ void k_u8_to_planes(const uint8_t* __restrict__ in, size_t step, size_t lane_stride, int w, int h,
+                               float* __restrict__ out, int pitch, size_t plane) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, lane = blockIdx.z;
+    if (x >= w) return;
+    const uint8_t* p = in + (size_t)lane * lane_stride + (size_t)y * step + (size_t)x * C;
+#pragma unroll
+    for (int c = 0; c < C; ++c) out[(size_t)(lane * C + c) * plane + (size_t)y * pitch + x] = (float)__ldg(p + c);
+}
+
+// small pyramid level (pitched planes) -> one time slot of the ring, rows packed tight
+__global__ void k_ring_append(const float* __restrict__ src, int w, int h, int pitch, size_t plane,
+                              float* __restrict__ slot, int planes) {
+    const size_t n = (size_t)planes * h * w;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int pl = (int)(i / ((size_t)h * w));
+        const int rem = (int)(i - (size_t)pl * h * w);
+        const int y = rem / w, x = rem - y * w;
+        slot[i] = src[(size_t)pl * plane + (size_t)y * pitch + x];
+    }
+}
+
+// spectrum[k][i] *= mask[k]  (mulSpectrums with the CCS-packed 0/1 mask, TemporalFilter.cpp:45-48)
+__global__ void k_mask_mul(float2* __restrict__ spec, size_t S, int nbins, const float2* __restrict__ mask) {
+    const size_t n = S * nbins;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int k = (int)(i / S);
+        const float2 m = mask[k];
+        const float2 v = spec[i];
+        spec[i] = make_float2(v.x * m.x - v.y * m.y, v.x * m.y + v.y * m.x);
+    }
+}
+
+// per-lane min/max over `nchunks` chunks of `chunk` contiguous floats (chunk t at base + t*chunk_stride + lane*chunk)
+__global__ void k_minmax(const float* __restrict__ base, size_t chunk, int nchunks, size_t chunk_stride,
+                         unsigned* __restrict__ mm) {
+    const int lane = blockIdx.y;
+    float mn = INFINITY, mx = -INFINITY;
+    const size_t total = chunk * (size_t)nchunks;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t t = i / chunk, r = i - t * chunk;
+        const float v = base[t * chunk_stride + (size_t)lane * chunk + r];
+        mn = fminf(mn, v);
+        mx = fmaxf(mx, v);
+    }
+    for (int o = 16; o; o >>= 1) {
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(&mm[2 * lane], f2ord(mn));
+        atomicMax(&mm[2 * lane + 1], f2ord(mx));
+    }
+}
+
+// filtered column -> normalize(0,1,MINMAX) -> * alpha -> pitched planes (TemporalFilter.cpp:55, MagnifyCore.hpp:185-192)
+__global__ void k_select(const float* __restrict__ col, const unsigned* __restrict__ mm, int C, int w, int h,
+                         float alpha, float* __restrict__ dst, int pitch, size_t plane, int planes) {
+    const size_t n = (size_t)planes * h * w;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int pl = (int)(i / ((size_t)h * w));
+        const int rem = (int)(i - (size_t)pl * h * w);
+        const int y = rem / w, x = rem - y * w;
+        const int lane = pl / C;
+        const double smin = (double)ord2f(mm[2 * lane]), smax = (double)ord2f(mm[2 * lane + 1]);
+        const double scale = (smax - smin > DBL_EPSILON) ? 1.0 / (smax - smin) : 0.0;   // cv::normalize NORM_MINMAX
+        const double shift = 0.0 - smin * scale;
+        const float v = fmaf(col[i], (float)scale, (float)shift);
+        dst[(size_t)pl * plane + (size_t)y * pitch + x] = v * alpha;
+    }
+}
+
+// cv::pyrUp with the default destination size 2w x 2h (SpatialFilter.cpp:45)
+__global__ void __launch_bounds__(256) k_pyrup2x(Level ls, Level ld, const float* __restrict__ src,
+                                                 float* __restrict__ dst) {
+    __shared__ float sD[10][34];
+    __shared__ float sU[10][64];
+    const int plane = blockIdx.z;
+    const int x0 = blockIdx.x * 64, y0 = blockIdx.y * 16;
+    const float* __restrict__ s = src + (size_t)plane * ls.plane;
+    for (int idx = threadIdx.x; idx < 10 * 34; idx += blockDim.x) {
+        const int k = idx / 34, j = idx - k * 34;
+        const int iy = upsrc(y0 / 2 - 1 + k, ls.h), ix = upsrc(x0 / 2 - 1 + j, ls.w);
+        sD[k][j] = __ldg(s + (size_t)iy * ls.pitch + ix);
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < 10 * 64; idx += blockDim.x) {
+        const int k = idx / 64, x = idx - k * 64;
+        const int j0 = (x >> 1) + 1;
+        sU[k][x] = (x & 1) ? (sD[k][j0] + sD[k][j0 + 1]) * 4.0f : (sD[k][j0 - 1] + sD[k][j0] * 6.0f + sD[k][j0 + 1]);
+    }
+    __syncthreads();
+    float* __restrict__ d = dst + (size_t)plane * ld.plane;
+    for (int idx = threadIdx.x; idx < 16 * 64; idx += blockDim.x) {
+        const int y = idx / 64, x = idx - y * 64;
+        const int gy = y0 + y, gx = x0 + x;
+        if (gy >= ld.h || gx >= ld.w) continue;
+        const int k0 = (y >> 1) + 1;
+        d[(size_t)gy * ld.pitch + gx] = (y & 1) ? ((sU[k0][x] + sU[k0 + 1][x]) * 4.0f) * (1.0f / 64.0f)
+                                                 : (sU[k0 - 1][x] + sU[k0][x] * 6.0f + sU[k0 + 1][x]) * (1.0f / 64.0f);
+    }
+}
+
+// cv::resize(INTER_LINEAR) on f32 planes (SpatialFilter.cpp:48): horizontal then vertical lerp
+__global__ void k_resize_linear(Level ls, Level ld, const float* __restrict__ src, float* __restrict__ dst) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, plane = blockIdx.z;
+    if (x >= ld.w) return;
+    const double sx_scale = (double)ls.w / ld.w, sy_scale = (double)ls.h / ld.h;
+    float fx = (float)((x + 0.5) * sx_scale - 0.5);
+    int sx = (int)floorf(fx);
+    fx -= sx;
+    if (sx < 0) { fx = 0.f; sx = 0; }
+    if (sx >= ls.w - 1) { fx = 0.f; sx = ls.w - 1; }
+    float fy = (float)((y + 0.5) * sy_scale - 0.5);
+    int sy = (int)floorf(fy);
+    fy -= sy;
+    if (sy < 0) { fy = 0.f; sy = 0; }
+    if (sy >= ls.h - 1) { fy = 0.f; sy = ls.h - 1; }
+    const int sx1 = min(sx + 1, ls.w - 1), sy1 = min(sy + 1, ls.h - 1);
+    const float* s = src + (size_t)plane * ls.plane;
+    const float r0 = s[(size_t)sy * ls.pitch + sx] * (1.f - fx) + s[(size_t)sy * ls.pitch + sx1] * fx;
+    const float r1 = s[(size_t)sy1 * ls.pitch + sx] * (1.f - fx) + s[(size_t)sy1 * ls.pitch + sx1] * fx;
+    dst[(size_t)plane * ld.plane + (size_t)y * ld.pitch + x] = r0 * (1.f - fy) + r1 * fy;
+}
+
+// min/max of output = input + colorImg per lane (MagnifyCore.hpp:197-201)
+__global__ void k_sum_minmax(const float* __restrict__ a, const float* __restrict__ b, Level l, int C,
+                             unsigned* __restrict__ mm) {
+    const int lane = blockIdx.y;
+    float mn = INFINITY, mx = -INFINITY;
+    const size_t total = (size_t)C * l.h * l.w;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i / ((size_t)l.h * l.w));
+        const int rem = (int)(i - (size_t)c * l.h * l.w);
+        const int y = rem / l.w, x = rem - y * l.w;
+        const size_t o = (size_t)(lane * C + c) * l.plane + (size_t)y * l.pitch + x;
+        const float v = a[o] + b[o];
+        mn = fminf(mn, v);
+        mx = fmaxf(mx, v);
+    }
+    for (int o = 16; o; o >>= 1) {
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(&mm[2 * lane], f2ord(mn));
+        atomicMax(&mm[2 * lane + 1], f2ord(mx));
+    }
+}
+
+// out8u = convertTo(input + colorImg, 255/(max-min), -min*255/(max-min))  (MagnifyCore.hpp:202-203)
+template <int C>
+__global__ void k_color_egress(const float* __restrict__ a, const float* __restrict__ b, Level l,
+                               const unsigned* __restrict__ mm, uint8_t* __restrict__ out, size_t step,
+                               size_t lane_stride, float* __restrict__ fout) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, lane = blockIdx.z;
+    if (x >= l.w) return;
+    const double mn = (double)ord2f(mm[2 * lane]), mx = (double)ord2f(mm[2 * lane + 1]);
+    const float sa = (float)(255.0 / (mx - mn)), sb = (float)(-mn * 255.0 / (mx - mn));
+    uint8_t* q = out + (size_t)lane * lane_stride + (size_t)y * step + (size_t)x * C;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        const size_t o = (size_t)(lane * C + c) * l.plane + (size_t)y * l.pitch + x;
+        const float v = a[o] + b[o];
+        q[c] = scaled_to_u8(v, sa, sb);
+        if (fout) fout[(((size_t)lane * l.h + y) * l.w + x) * C + c] = v;
+    }
+}
+
+inline unsigned cdiv(int a, int b) { return (unsigned)((a + b - 1) / b); }
+inline unsigned gs_blocks(size_t n) {
+    size_t b = (n + 255) / 256;
+    return (unsigned)(b < 1 ? 1 : (b > 148 * 16 ? 148 * 16 : b));
+}
+
+}  // namespace
+
+void ColorMode::reset() {
+    if (plan_r2c) cufftDestroy(plan_r2c);
+    if (plan_c2r) cufftDestroy(plan_c2r);
+    plan_r2c = plan_c2r = 0;
+    plan_n = 0;
+    arena.release();
+    lv.clear(); G.clear(); U.clear(); ulv.clear();
+    ring = work = nullptr; spec = nullptr; minmax = nullptr; filtered_small = nullptr;
+    allocated = false;
+    count = head = cap = 0;
+    ring_cap = 0;
+    mask_dev = nullptr;
+    mask_cap = 0;
+}
+
+#define CUFFT_CK(call)                                                            \
+    do {                                                                          \
+        cufftResult r__ = (call);                                                 \
+        if (r__ != CUFFT_SUCCESS) {                                               \
+            *ctx.err = std::string(#call) + ": cufft error " + std::to_string((int)r__); \
+            return MC_ERR_CUDA;                                                   \
+        }                                                                         \
+    } while (0)
+
+mc_status ColorMode::process(const ModeCtx& ctx, const FrameIO& io, const mc_params& p, int nlevels, int* produced) {
+    *produced = 0;
+    const int want_cap = optimal_buffer_size((int)p.framerate);  // MagnifyCore.hpp:176
+    const int C = io.channels;
+    const int planes = lanes * C;
+    if (!allocated) {
+        reset();
+        levels = nlevels; channels = C; w = io.w; h = io.h;
+        lv.resize((size_t)levels + 1);
+        int cw = w, ch = h;
+        for (int l = 0; l <= levels; ++l) {
+            lv[(size_t)l] = make_level(cw, ch);
+            cw = (cw + 1) / 2; ch = (ch + 1) / 2;
+        }
+        G.assign((size_t)levels + 1, nullptr);
+        for (int l = 0; l <= levels; ++l) MCK(arena.alloc(&G[(size_t)l], (size_t)planes * lv[(size_t)l].plane));
+        const Level& ls = lv[(size_t)levels];
+        small_rows = ls.w * ls.h;
+        ulv.resize((size_t)levels + 1);
+        U.assign((size_t)levels + 2, nullptr);
+        int uw = ls.w, uh = ls.h;
+        for (int i = 0; i <= levels; ++i) {
+            ulv[(size_t)i] = make_level(uw, uh);
+            MCK(arena.alloc(&U[(size_t)i], (size_t)planes * ulv[(size_t)i].plane));
+            uw *= 2; uh *= 2;
+        }
+        if (ulv[(size_t)levels].w != w || ulv[(size_t)levels].h != h)
+            MCK(arena.alloc(&U[(size_t)levels + 1], (size_t)planes * lv[0].plane));
+        void* mmv = nullptr;
+        MCK(arena.alloc_bytes(&mmv, sizeof(unsigned) * 4 * (size_t)lanes));
+        minmax = (float*)mmv;
+        allocated = true;
+    }
+    const size_t S = (size_t)planes * small_rows;  // signals (pixels x channels x lanes)
+    // ring capacity: grows when the framerate asks for a longer window (rare); contents are kept in
+    // logical order so the invariant "head == 0 or count == capacity" holds.
+    if (cap < want_cap || ring == nullptr) {
+        const int new_cap = std::max(want_cap, std::max(cap, 2));
+        float *nring = nullptr, *nwork = nullptr;
+        void* nspec = nullptr;
+        MCK(arena.alloc(&nring, (size_t)new_cap * S));
+        MCK(arena.alloc(&nwork, (size_t)new_cap * S));
+        MCK(arena.alloc_bytes(&nspec, sizeof(cufftComplex) * (size_t)(new_cap / 2 + 1) * S));
+        for (int t = 0; t < count; ++t)
+            MCK(cudaMemcpyAsync(nring + (size_t)t * S, ring + (size_t)((head + t) % cap) * S, S * sizeof(float),
+                                cudaMemcpyDeviceToDevice, ctx.stream));
+        ring = nring; work = nwork; spec = (cufftComplex*)nspec;
+        head = 0;
+        ring_cap = new_cap;
+    }
+    cap = std::max(cap, want_cap);
+
+    // ingest + Gaussian chain (SpatialFilter.cpp:13-23)
+    {
+        dim3 grid(cdiv(w, 256), h, lanes);
+        if (C == 3) { const bool pp = ctx.prof && ctx.prof->begin("u8_to_planes", 0, ctx.stream); k_u8_to_planes<3><<<grid, 256, 0, ctx.stream>>>(io.in, io.in_step, io.in_lane_stride, w, h, G[0], lv[0].pitch, lv[0].plane); if (pp) ctx.prof->end(ctx.stream); }
+        else { const bool pp = ctx.prof && ctx.prof->begin("u8_to_planes", 0, ctx.stream); k_u8_to_planes<1><<<grid, 256, 0, ctx.stream>>>(io.in, io.in_step, io.in_lane_stride, w, h, G[0], lv[0].pitch, lv[0].plane); if (pp) ctx.prof->end(ctx.stream); }
+        MCK(cudaGetLastError());
+        ++*ctx.launches;
+    }
+    for (int l = 0; l < levels; ++l) {
+        LevelArgs a;
+        a.in_kind = 0; a.g = G[(size_t)l]; a.in_plane = lv[(size_t)l].plane; a.in_row = lv[(size_t)l].pitch;
+        a.channels = C; a.lf = lv[(size_t)l]; a.lc = lv[(size_t)l + 1]; a.g_next = G[(size_t)l + 1];
+        a.planes = planes; a.band = 0;
+        LAUNCH("gauss_down", l, launch_level(a, ctx.stream));
+    }
+    // append to the rolling window; once full drop the oldest column (SpatialFilter.cpp:63-84)
+    const Level& ls = lv[(size_t)levels];
+    {
+        const int slot = (head + count) % ring_cap;
+        const bool pp = ctx.prof && ctx.prof->begin("ring_append", 0, ctx.stream);
+        k_ring_append<<<gs_blocks(S), 256, 0, ctx.stream>>>(G[(size_t)levels], ls.w, ls.h, ls.pitch, ls.plane, ring + (size_t)slot * S, planes);
+        if (pp) ctx.prof->end(ctx.stream);
+        MCK(cudaGetLastError());
+        ++*ctx.launches;
+        ++count;
+        if (count > want_cap && want_cap > 0) {
+            head = (head + 1) % ring_cap;
+            --count;
+        }
+    }
+    if (count < 2) return MC_OK;  // MagnifyCore.hpp:180 (passthrough)
+    const int n = count;
+    if (head != 0 && n != ring_cap) {
+        // window is not cyclically contiguous (capacity grew beyond a shrunk window): compact it
+        *ctx.err = "color window: unsupported capacity change";
+        return MC_ERR_UNSUPPORTED;
+    }
+
+    // ideal temporal band-pass (TemporalFilter.cpp:24-57) on the physical column order
+    if (plan_n != n) {
+        if (plan_r2c) cufftDestroy(plan_r2c);
+        if (plan_c2r) cufftDestroy(plan_c2r);
+        plan_r2c = plan_c2r = 0;
+        int nn[1] = {n};
+        int inembed[1] = {n}, onembed[1] = {n / 2 + 1};
+        CUFFT_CK(cufftPlanMany(&plan_r2c, 1, nn, inembed, (int)S, 1, onembed, (int)S, 1, CUFFT_R2C, (int)S));
+        CUFFT_CK(cufftPlanMany(&plan_c2r, 1, nn, onembed, (int)S, 1, inembed, (int)S, 1, CUFFT_C2R, (int)S));
+        CUFFT_CK(cufftSetStream(plan_r2c, ctx.stream));
+        CUFFT_CK(cufftSetStream(plan_c2r, ctx.stream));
+        plan_n = n;
+    }
+    {
+        double lo = p.coLow, hi = p.coHigh;
+        if (lo == 0.0) lo += 0.01;  // TemporalFilter.cpp:26-27
+        // createIdealBandpassFilter (TemporalFilter.cpp:59-80): real 0/1 mask over packed indices x,
+        // read back by mulSpectrums as the complex number m[2k-1] + i m[2k] per bin.
+        const float width = (float)n;
+        const double fl = 2 * lo * width / p.framerate, fh = 2 * hi * width / p.framerate;
+        auto m = [&](int x) { return (x >= fl && x <= fh) ? 1.0f : 0.0f; };
+        std::vector<float2> mask((size_t)n / 2 + 1);
+        const float sc = 1.0f / ((float)n * (float)n);  // DFT_SCALE on both transforms
+        mask[0] = make_float2(m(0) * sc, 0.f);
+        for (int k = 1; k <= n / 2; ++k) {
+            if (2 * k == n) mask[(size_t)k] = make_float2(m(n - 1) * sc, 0.f);       // Nyquist: real only
+            else mask[(size_t)k] = make_float2(m(2 * k - 1) * sc, m(2 * k) * sc);
+        }
+        if (!mask_dev || mask_cap < (int)mask.size()) {
+            void* mv = nullptr;
+            MCK(arena.alloc_bytes(&mv, sizeof(float2) * (size_t)(ring_cap / 2 + 2)));
+            mask_dev = mv; mask_cap = ring_cap / 2 + 2;
+        }
+        MCK(cudaMemcpyAsync(mask_dev, mask.data(), sizeof(float2) * mask.size(), cudaMemcpyHostToDevice, ctx.stream));
+    }
+    {
+        const bool pp = ctx.prof && ctx.prof->begin("cufft_r2c", 0, ctx.stream);
+        CUFFT_CK(cufftExecR2C(plan_r2c, ring, spec));
+        if (pp) ctx.prof->end(ctx.stream);
+        ++*ctx.launches;
+    }
+    {
+        const bool pp = ctx.prof && ctx.prof->begin("mask_mul", 0, ctx.stream);
+        k_mask_mul<<<gs_blocks(S * (size_t)(n / 2 + 1)), 256, 0, ctx.stream>>>((float2*)spec, S, n / 2 + 1, (const float2*)mask_dev);
+        if (pp) ctx.prof->end(ctx.stream);
+        MCK(cudaGetLastError());
+        ++*ctx.launches;
+    }
+    {
+        const bool pp = ctx.prof && ctx.prof->begin("cufft_c2r", 0, ctx.stream);
+        CUFFT_CK(cufftExecC2R(plan_c2r, spec, work));
+        if (pp) ctx.prof->end(ctx.stream);
+        ++*ctx.launches;
+    }
+    unsigned* mm = (unsigned*)minmax;
+    k_mm_init<<<1, 256, 0, ctx.stream>>>(mm, 4 * lanes);
+    MCK(cudaGetLastError());
+    ++*ctx.launches;
+    {
+        // global min/max per stream over all pixels, frames and channels (TemporalFilter.cpp:55)
+        dim3 grid(gs_blocks((size_t)C * small_rows * n) / 2 + 1, lanes);
+        const bool pp = ctx.prof && ctx.prof->begin("minmax_window", 0, ctx.stream);
+        k_minmax<<<grid, 256, 0, ctx.stream>>>(work, (size_t)C * small_rows, n, S, mm);
+        if (pp) ctx.prof->end(ctx.stream);
+        MCK(cudaGetLastError());
+        ++*ctx.launches;
+    }
+    // the reconstructed column is logical index min(1, n-1) (MagnifyCore.hpp:189-192)
+    const int logical = std::min(1, n - 1);
+    const int phys = (head + logical) % ring_cap;
+    {
+        const bool pp = ctx.prof && ctx.prof->begin("select", 0, ctx.stream);
+        k_select<<<gs_blocks(S), 256, 0, ctx.stream>>>(work + (size_t)phys * S, mm, C, ls.w, ls.h, (float)p.amplification, U[0], ulv[0].pitch, ulv[0].plane, planes);
+        if (pp) ctx.prof->end(ctx.stream);
+        MCK(cudaGetLastError());
+        ++*ctx.launches;
+    }
+    // pyrUp chain with default 2x sizes, then bilinear resize to the frame size (SpatialFilter.cpp:40-50)
+    for (int i = 0; i < levels; ++i) {
+        const Level& s0 = ulv[(size_t)i];
+        const Level& d0 = ulv[(size_t)i + 1];
+        dim3 grid(cdiv(d0.w, 64), cdiv(d0.h, 16), planes);
+        const bool pp = ctx.prof && ctx.prof->begin("pyrup2x", i, ctx.stream);
+        k_pyrup2x<<<grid, 256, 0, ctx.stream>>>(s0, d0, U[(size_t)i], U[(size_t)i + 1]);
+        if (pp) ctx.prof->end(ctx.stream);
+        MCK(cudaGetLastError());
+        ++*ctx.launches;
+    }
+    const float* color_img = U[(size_t)levels];
+    if (U[(size_t)levels + 1]) {
+        dim3 grid(cdiv(w, 256), h, planes);
+        const bool pp = ctx.prof && ctx.prof->begin("resize", 0, ctx.stream);
+        k_resize_linear<<<grid, 256, 0, ctx.stream>>>(ulv[(size_t)levels], lv[0], U[(size_t)levels], U[(size_t)levels + 1]);
+        if (pp) ctx.prof->end(ctx.stream);
+        MCK(cudaGetLastError());
+        ++*ctx.launches;
+        color_img = U[(size_t)levels + 1];
+    }
+    {
+        dim3 grid(gs_blocks((size_t)C * w * h) / 2 + 1, lanes);
+        const bool pp = ctx.prof && ctx.prof->begin("minmax_out", 0, ctx.stream);
+        k_sum_minmax<<<grid, 256, 0, ctx.stream>>>(G[0], color_img, lv[0], C, mm + 2 * lanes);
+        if (pp) ctx.prof->end(ctx.stream);
+        MCK(cudaGetLastError());
+        ++*ctx.launches;
+    }
+    {
+        dim3 grid(cdiv(w, 256), h, lanes);
+        const bool pp = ctx.prof && ctx.prof->begin("color_egress", 0, ctx.stream);
+        if (C == 3) k_color_egress<3><<<grid, 256, 0, ctx.stream>>>(G[0], color_img, lv[0], mm + 2 * lanes, io.out, io.out_step, io.out_lane_stride, ctx.float_out);
+        else k_color_egress<1><<<grid, 256, 0, ctx.stream>>>(G[0], color_img, lv[0], mm + 2 * lanes, io.out, io.out_step, io.out_lane_stride, ctx.float_out);
+        if (pp) ctx.prof->end(ctx.stream);
+        MCK(cudaGetLastError());
+        ++*ctx.launches;
+    }
+    *produced = 1;
+    return MC_OK;
+}
+
 void ColorMode::find_state(const char*, int, StateRef& out) { out = StateRef{}; }
+
 }  // namespace mc

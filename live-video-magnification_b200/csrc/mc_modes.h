@@ -109,6 +109,9 @@ struct ColorMode {
     float* minmax = nullptr;    // device scalars
     float* filtered_small = nullptr;
     int small_rows = 0;         // pixels of the small level
+    int ring_cap = 0;           // physical slots allocated
+    void* mask_dev = nullptr;
+    int mask_cap = 0;
     cufftHandle plan_r2c = 0, plan_c2r = 0;
     int plan_n = 0;
     DeviceArena arena;
