@@ -126,22 +126,26 @@ struct RieszMode {
     bool allocated = false;     // st.cur != null
     int levels = 0, w = 0, h = 0;
     double lo_freq = 0, hi_freq = 0, framerate = 0;   // itsFrequency / itsFramerate of the two filters
-    double loA[3] = {0, 0, 0}, loB[3] = {0, 0, 0}, hiA[3] = {0, 0, 0}, hiB[3] = {0, 0, 0};
-    std::vector<Level> lv;
+    double loA[3] = {1, 0, 0}, loB[3] = {0, 0, 0}, hiA[3] = {1, 0, 0}, hiB[3] = {0, 0, 0};
+    std::vector<Level> lv;      // octave sizes, 0..levels-1 (band levels 0..levels-2 + low-pass residual)
     DeviceArena arena;
-    // per level planes (lanes planes each)
-    std::vector<float*> cur_low, cur_rx, cur_ry, old_low, old_rx, old_ry;
-    std::vector<float*> oct;                       // octave (input of each level)
-    std::vector<float*> phase_c, phase_s;          // accumulated phase (shared by both filters: identical)
-    std::vector<float*> lo_r0c, lo_r0s, lo_r1c, lo_r1s, hi_r0c, hi_r0s, hi_r1c, hi_r1s;
-    std::vector<float*> amp, t_c, t_s;             // amplitude, (hi-lo)*A cos/sin
-    std::vector<float*> amp_blur, tb_c, tb_s, tmp0, tmp1, tmp2;
-    std::vector<float*> lab;                       // a,b planes + L
-    float *Lplane = nullptr, *Aplane = nullptr, *Bplane = nullptr, *collapse_a = nullptr, *collapse_b = nullptr;
+    // per level planes (one plane per lane: only L is processed)
+    std::vector<float*> oct;                                  // octave i (input of level i); oct[levels-1] is the residual
+    std::vector<float*> cur_low, cur_rx, cur_ry;              // this frame's band + Riesz pair
+    std::vector<float*> old_low, old_rx, old_ry;              // prior pyramid (RieszState::old)
+    std::vector<float*> phase_c, phase_s;                     // accumulated phase (the two filters' copies are identical)
+    std::vector<float*> lo_r0c, lo_r0s, lo_r1c, lo_r1s, hi_r0c, hi_r0s, hi_r1c, hi_r1s;   // DF-II registers
+    std::vector<float*> amp, t_c, t_s, low_amp, res;
+    int16_t* lab16 = nullptr;
+    int pitch16 = 0;
+    size_t plane16 = 0;
 
     void reset();
     mc_status process(const ModeCtx& ctx, const FrameIO& io, const mc_params& p, int levels, int* produced);
     void find_state(const char* name, int level, StateRef& out);
+
+private:
+    mc_status build_pyramid(const ModeCtx& ctx);
 };
 
 }  // namespace mc

@@ -1,11 +1,498 @@
-// Phase (Riesz) mode — placeholder until the Riesz pyramid path lands.
+// Phase (Riesz) mode — device twin of magcore::magnifyRiesz (reference
+// src/processing/magnification/MagnifyCore.hpp:209-279) with RieszPyramid.cpp / TemporalFilter.cpp:299-362.
+//
+//   analysis : 9x9 high-pass band + 9x9 2*low-pass, subsampled            (RieszPyramid.cpp:215-238)
+//   phase    : Riesz pair (1x5 / 5x1) + quaternionic phase difference +
+//              amplitude + both 2nd-order Butterworth IIRs (DF-II)         (RieszPyramid.cpp:66-111, TemporalFilter.cpp:340-351)
+//   amplify  : separable 13-tap Gaussian of (A, cos, sin) + phase shift    (RieszPyramid.cpp:114-144)
+//   collapse : zero-injected 2*LP up-sampling + HP of the band, summed     (RieszPyramid.cpp:304-325)
+//   egress   : merge L' with a,b -> Lab2BGR -> u8                           (MagnifyCore.hpp:272-276)
+//
+// The point-wise quaternion algebra uses explicit round-to-nearest intrinsics (no FMA contraction)
+// so that, given identical inputs, it rounds exactly like OpenCV's element-wise cv::multiply / add /
+// divide / sqrt calls — acos near 1 is ill-conditioned.
+#include <cmath>
+#include <cstring>
+
 #include "mc_modes.h"
+
 namespace mc {
-void RieszMode::reset() { arena.release(); allocated = false; }
-mc_status RieszMode::process(const ModeCtx& ctx, const FrameIO&, const mc_params&, int, int* produced) {
-    *produced = 0;
-    *ctx.err = "Phase mode not implemented yet";
-    return MC_ERR_UNSUPPORTED;
+
+namespace {
+
+// literal 4-decimal tap tables of the Riesz-pyramid paper, as the reference writes them
+// (RieszPyramid.cpp:146-167); the low-pass is used x2 on analysis and synthesis (:232, :316).
+__constant__ float c_hp[81] = {
+    0.0000f, 0.0003f, 0.0011f, 0.0022f, 0.0027f, 0.0022f, 0.0011f, 0.0003f, 0.0000f,
+    0.0003f, 0.0020f, 0.0059f, 0.0103f, 0.0123f, 0.0103f, 0.0059f, 0.0020f, 0.0003f,
+    0.0011f, 0.0059f, 0.0151f, 0.0249f, 0.0292f, 0.0249f, 0.0151f, 0.0059f, 0.0011f,
+    0.0022f, 0.0103f, 0.0249f, 0.0402f, 0.0469f, 0.0402f, 0.0249f, 0.0103f, 0.0022f,
+    0.0027f, 0.0123f, 0.0292f, 0.0469f, -0.9455f, 0.0469f, 0.0292f, 0.0123f, 0.0027f,
+    0.0022f, 0.0103f, 0.0249f, 0.0402f, 0.0469f, 0.0402f, 0.0249f, 0.0103f, 0.0022f,
+    0.0011f, 0.0059f, 0.0151f, 0.0249f, 0.0292f, 0.0249f, 0.0151f, 0.0059f, 0.0011f,
+    0.0003f, 0.0020f, 0.0059f, 0.0103f, 0.0123f, 0.0103f, 0.0059f, 0.0020f, 0.0003f,
+    0.0000f, 0.0003f, 0.0011f, 0.0022f, 0.0027f, 0.0022f, 0.0011f, 0.0003f, 0.0000f,
+};
+__constant__ float c_lp[81] = {
+    -0.0001f, -0.0007f, -0.0023f, -0.0046f, -0.0057f, -0.0046f, -0.0023f, -0.0007f, -0.0001f,
+    -0.0007f, -0.0030f, -0.0047f, -0.0025f, -0.0003f, -0.0025f, -0.0047f, -0.0030f, -0.0007f,
+    -0.0023f, -0.0047f, 0.0054f, 0.0272f, 0.0387f, 0.0272f, 0.0054f, -0.0047f, -0.0023f,
+    -0.0046f, -0.0025f, 0.0272f, 0.0706f, 0.0910f, 0.0706f, 0.0272f, -0.0025f, -0.0046f,
+    -0.0057f, -0.0003f, 0.0387f, 0.0910f, 0.1138f, 0.0910f, 0.0387f, -0.0003f, -0.0057f,
+    -0.0046f, -0.0025f, 0.0272f, 0.0706f, 0.0910f, 0.0706f, 0.0272f, -0.0025f, -0.0046f,
+    -0.0023f, -0.0047f, 0.0054f, 0.0272f, 0.0387f, 0.0272f, 0.0054f, -0.0047f, -0.0023f,
+    -0.0007f, -0.0030f, -0.0047f, -0.0025f, -0.0003f, -0.0025f, -0.0047f, -0.0030f, -0.0007f,
+    -0.0001f, -0.0007f, -0.0023f, -0.0046f, -0.0057f, -0.0046f, -0.0023f, -0.0007f, -0.0001f,
+};
+
+constexpr int RT_W = 32, RT_H = 16;                 // output tile
+constexpr int RA_W = RT_W + 8, RA_H = RT_H + 8;     // + 4 halo for 9x9
+
+__device__ __forceinline__ float mulr(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float addr(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float subr(float a, float b) { return __fsub_rn(a, b); }
+
+__global__ void k_s16_to_f32(const int16_t* __restrict__ src, int pitch16, size_t plane16, int plane_step,
+                             float scale, float off, Level l, float* __restrict__ dst) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, lane = blockIdx.z;
+    if (x >= l.w) return;
+    const float v = (float)src[(size_t)lane * plane_step * plane16 + (size_t)y * pitch16 + x];
+    dst[(size_t)lane * l.plane + (size_t)y * l.pitch + x] = fmaf(v, scale, off);
 }
-void RieszMode::find_state(const char*, int, StateRef& out) { out = StateRef{}; }
+
+// hp = filter2D(oct, HP) ; next = subsample(filter2D(oct, 2*LP))   (REFLECT_101, correlation)
+__global__ void __launch_bounds__(256) k_riesz_analysis(Level l, Level ln, const float* __restrict__ oct,
+                                                        float* __restrict__ hp, float* __restrict__ next) {
+    __shared__ float s[RA_H][RA_W + 1];
+    const int plane = blockIdx.z;
+    const int x0 = blockIdx.x * RT_W, y0 = blockIdx.y * RT_H;
+    const float* __restrict__ src = oct + (size_t)plane * l.plane;
+    for (int i = threadIdx.x; i < RA_H * RA_W; i += 256) {
+        const int r = i / RA_W, c = i - r * RA_W;
+        s[r][c] = __ldg(src + (size_t)reflect101(y0 - 4 + r, l.h) * l.pitch + reflect101(x0 - 4 + c, l.w));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < RT_H * RT_W; i += 256) {
+        const int y = i / RT_W, x = i - y * RT_W;
+        const int gy = y0 + y, gx = x0 + x;
+        if (gy >= l.h || gx >= l.w) continue;
+        float acc = 0.f;
+#pragma unroll
+        for (int ky = 0; ky < 9; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 9; ++kx) acc = fmaf(c_hp[ky * 9 + kx], s[y + ky][x + kx], acc);
+        hp[(size_t)plane * l.plane + (size_t)gy * l.pitch + gx] = acc;
+        if (next && !(gy & 1) && !(gx & 1)) {
+            float a2 = 0.f;
+#pragma unroll
+            for (int ky = 0; ky < 9; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < 9; ++kx) a2 = fmaf(2.0f * c_lp[ky * 9 + kx], s[y + ky][x + kx], a2);
+            next[(size_t)plane * ln.plane + (size_t)(gy >> 1) * ln.pitch + (gx >> 1)] = a2;
+        }
+    }
+}
+
+struct Butter { double b0, b1, b2, a1, a2; };
+
+struct PhaseArgs {
+    Level l;
+    const float* low;                      // this frame's band (hp)
+    const float *plow, *prx, *pry;         // prior pyramid (old); null -> use this frame's (cutoff change)
+    float *rx, *ry;                        // this frame's Riesz pair (written)
+    float *ph_c, *ph_s;                    // accumulated phase
+    float *lo_r0c, *lo_r0s, *lo_r1c, *lo_r1s, *hi_r0c, *hi_r0s, *hi_r1c, *hi_r1s;
+    float *amp, *t_c, *t_s;                // amplitude, (hiIIR - loIIR) * amplitude
+    Butter lo, hi;
+};
+
+__device__ __forceinline__ float muld(float x, double s) { return (float)((double)x * s); }  // cv::multiply(Mat, double)
+
+__device__ __forceinline__ float iir_step(float phase, float& r0, float& r1, const Butter& k) {
+    // RieszTemporalFilter::IIRTemporalFilter (TemporalFilter.cpp:340-351), Direct Form II
+    const float y = addr(muld(phase, k.b0), r0);
+    r0 = subr(addr(muld(phase, k.b1), r1), muld(y, k.a1));
+    r1 = subr(muld(phase, k.b2), muld(y, k.a2));
+    return y;
+}
+
+__global__ void __launch_bounds__(256) k_riesz_phase(const PhaseArgs a) {
+    __shared__ float s[RT_H + 4][RT_W + 4 + 1];
+    const int plane = blockIdx.z;
+    const int x0 = blockIdx.x * RT_W, y0 = blockIdx.y * RT_H;
+    const Level l = a.l;
+    const size_t pb = (size_t)plane * l.plane;
+    for (int i = threadIdx.x; i < (RT_H + 4) * (RT_W + 4); i += 256) {
+        const int r = i / (RT_W + 4), c = i - r * (RT_W + 4);
+        s[r][c] = __ldg(a.low + pb + (size_t)reflect101(y0 - 2 + r, l.h) * l.pitch + reflect101(x0 - 2 + c, l.w));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < RT_H * RT_W; i += 256) {
+        const int y = i / RT_W, x = i - y * RT_W;
+        const int gy = y0 + y, gx = x0 + x;
+        if (gy >= l.h || gx >= l.w) continue;
+        const size_t o = pb + (size_t)gy * l.pitch + gx;
+        // RieszPyramidLevel::build (RieszPyramid.cpp:66-78): taps [-0.2, -0.48, 0, 0.48, 0.2]
+        const float low = s[y + 2][x + 2];
+        float rx = -0.2f * s[y + 2][x];
+        rx = fmaf(-0.48f, s[y + 2][x + 1], rx);
+        rx = fmaf(0.48f, s[y + 2][x + 3], rx);
+        rx = fmaf(0.2f, s[y + 2][x + 4], rx);
+        float ry = -0.2f * s[y][x + 2];
+        ry = fmaf(-0.48f, s[y + 1][x + 2], ry);
+        ry = fmaf(0.48f, s[y + 3][x + 2], ry);
+        ry = fmaf(0.2f, s[y + 4][x + 2], ry);
+        a.rx[o] = rx;
+        a.ry[o] = ry;
+        const float plow = a.plow ? a.plow[o] : low;
+        const float prx = a.plow ? a.prx[o] : rx;
+        const float pry = a.plow ? a.pry[o] : ry;
+        // computePhaseDifferenceAndAmplitude (RieszPyramid.cpp:81-111)
+        const float q_real = addr(addr(mulr(low, plow), mulr(rx, prx)), mulr(ry, pry));
+        const float neg_low = -low;
+        const float qx = addr(mulr(prx, neg_low), mulr(rx, plow));
+        const float qy = addr(mulr(pry, neg_low), mulr(ry, plow));
+        const float xy_sq = addr(mulr(qx, qx), mulr(qy, qy));
+        const float q_amp = __fsqrt_rn(addr(mulr(q_real, q_real), xy_sq));
+        const float tmp = __fdiv_rn(q_real, q_amp);
+        float phi;
+        if (tmp < -1.0f) phi = -1.0f;           // reference quirk: clamps to +-1.0 *radians* (RieszPyramid.cpp:15-18)
+        else if (tmp > 1.0f) phi = 1.0f;
+        else phi = acosf(tmp);
+        const float xy_sqrt = __fsqrt_rn(xy_sq);
+        float pd_c = mulr(__fdiv_rn(qx, xy_sqrt), phi);
+        float pd_s = mulr(__fdiv_rn(qy, xy_sqrt), phi);
+        if (pd_c != pd_c) pd_c = 0.f;           // cv::patchNaNs
+        if (pd_s != pd_s) pd_s = 0.f;
+        const float amp = __fsqrt_rn(q_amp);
+        // temporal band-pass of the accumulated phase (MagnifyCore.hpp:259-264)
+        const float ph_c = addr(a.ph_c[o], pd_c), ph_s = addr(a.ph_s[o], pd_s);
+        a.ph_c[o] = ph_c;
+        a.ph_s[o] = ph_s;
+        float r0, r1;
+        r0 = a.lo_r0c[o]; r1 = a.lo_r1c[o];
+        const float lo_c = iir_step(ph_c, r0, r1, a.lo);
+        a.lo_r0c[o] = r0; a.lo_r1c[o] = r1;
+        r0 = a.lo_r0s[o]; r1 = a.lo_r1s[o];
+        const float lo_s = iir_step(ph_s, r0, r1, a.lo);
+        a.lo_r0s[o] = r0; a.lo_r1s[o] = r1;
+        r0 = a.hi_r0c[o]; r1 = a.hi_r1c[o];
+        const float hi_c = iir_step(ph_c, r0, r1, a.hi);
+        a.hi_r0c[o] = r0; a.hi_r1c[o] = r1;
+        r0 = a.hi_r0s[o]; r1 = a.hi_r1s[o];
+        const float hi_s = iir_step(ph_s, r0, r1, a.hi);
+        a.hi_r0s[o] = r0; a.hi_r1s[o] = r1;
+        // normalize(): change = highpassIIR - lowpassIIR ; result = change .* amplitude (RieszPyramid.cpp:118-120)
+        a.amp[o] = amp;
+        a.t_c[o] = mulr(subr(hi_c, lo_c), amp);
+        a.t_s[o] = mulr(subr(hi_s, lo_s), amp);
+    }
+}
+
+struct Gauss13 { float k[13]; };
+
+struct AmpArgs {
+    Level l;
+    const float *amp, *t_c, *t_s;          // inputs to blur
+    const float *low, *rx, *ry;            // this frame's band and Riesz pair
+    float* out;                            // amplified band
+    Gauss13 g;
+    float alpha, thresh;
+};
+
+constexpr int GA_W = RT_W + 12, GA_H = RT_H + 12;
+
+__global__ void __launch_bounds__(256) k_riesz_amplify(const AmpArgs a) {
+    __shared__ float s[3][GA_H][GA_W + 1];
+    __shared__ float sr[3][GA_H][RT_W + 1];
+    const int plane = blockIdx.z;
+    const int x0 = blockIdx.x * RT_W, y0 = blockIdx.y * RT_H;
+    const Level l = a.l;
+    const size_t pb = (size_t)plane * l.plane;
+    const float* srcs[3] = {a.amp, a.t_c, a.t_s};
+    for (int i = threadIdx.x; i < GA_H * GA_W; i += 256) {
+        const int r = i / GA_W, c = i - r * GA_W;
+        const size_t o = pb + (size_t)reflect101(y0 - 6 + r, l.h) * l.pitch + reflect101(x0 - 6 + c, l.w);
+#pragma unroll
+        for (int q = 0; q < 3; ++q) s[q][r][c] = __ldg(srcs[q] + o);
+    }
+    __syncthreads();
+    // row pass (symmetric kernel: centre + pairs, as cv::sepFilter2D's symmetric row filter)
+    for (int i = threadIdx.x; i < GA_H * RT_W; i += 256) {
+        const int r = i / RT_W, x = i - r * RT_W;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            float acc = a.g.k[6] * s[q][r][x + 6];
+#pragma unroll
+            for (int j = 1; j <= 6; ++j) acc = fmaf(a.g.k[6 + j], s[q][r][x + 6 - j] + s[q][r][x + 6 + j], acc);
+            sr[q][r][x] = acc;
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < RT_H * RT_W; i += 256) {
+        const int y = i / RT_W, x = i - y * RT_W;
+        const int gy = y0 + y, gx = x0 + x;
+        if (gy >= l.h || gx >= l.w) continue;
+        float b[3];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            float acc = a.g.k[6] * sr[q][y + 6][x];
+#pragma unroll
+            for (int j = 1; j <= 6; ++j) acc = fmaf(a.g.k[6 + j], sr[q][y + 6 - j][x] + sr[q][y + 6 + j][x], acc);
+            b[q] = acc;
+        }
+        const size_t o = pb + (size_t)gy * l.pitch + gx;
+        // normalize() tail + amplify() (RieszPyramid.cpp:125-143)
+        const float tc = __fdiv_rn(b[1], b[0]), ts = __fdiv_rn(b[2], b[0]);
+        const float mag = __fsqrt_rn(addr(mulr(tc, tc), mulr(ts, ts)));
+        float m2 = mulr(mag, a.alpha);
+        m2 = (m2 > a.thresh) ? a.thresh : m2;                 // THRESH_TRUNC
+        const float pc = cosf(m2), ps = sinf(m2);
+        float pair = __fdiv_rn(addr(mulr(a.rx[o], tc), mulr(a.ry[o], ts)), mag);
+        if (pair != pair) pair = 0.f;                          // patchNaNs
+        a.out[o] = subr(mulr(a.low[o], pc), mulr(pair, ps));
+    }
+}
+
+// result_i = filter2D(injectZerosEven(nearest_up(result_{i+1})), 2*LP) + filter2D(band_i, HP)
+__global__ void __launch_bounds__(256) k_riesz_collapse(Level l, Level lc, const float* __restrict__ band,
+                                                        const float* __restrict__ coarse, float* __restrict__ out) {
+    __shared__ float sb[RA_H][RA_W + 1];
+    __shared__ float su[RA_H][RA_W + 1];
+    const int plane = blockIdx.z;
+    const int x0 = blockIdx.x * RT_W, y0 = blockIdx.y * RT_H;
+    const float* __restrict__ b = band + (size_t)plane * l.plane;
+    const float* __restrict__ c = coarse + (size_t)plane * lc.plane;
+    for (int i = threadIdx.x; i < RA_H * RA_W; i += 256) {
+        const int r = i / RA_W, cc = i - r * RA_W;
+        const int gy = reflect101(y0 - 4 + r, l.h), gx = reflect101(x0 - 4 + cc, l.w);
+        sb[r][cc] = __ldg(b + (size_t)gy * l.pitch + gx);
+        su[r][cc] = ((gy | gx) & 1) ? 0.f : __ldg(c + (size_t)(gy >> 1) * lc.pitch + (gx >> 1));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < RT_H * RT_W; i += 256) {
+        const int y = i / RT_W, x = i - y * RT_W;
+        const int gy = y0 + y, gx = x0 + x;
+        if (gy >= l.h || gx >= l.w) continue;
+        float hp = 0.f, lp = 0.f;
+#pragma unroll
+        for (int ky = 0; ky < 9; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 9; ++kx) {
+                hp = fmaf(c_hp[ky * 9 + kx], sb[y + ky][x + kx], hp);
+                lp = fmaf(2.0f * c_lp[ky * 9 + kx], su[y + ky][x + kx], lp);
+            }
+        out[(size_t)plane * l.plane + (size_t)gy * l.pitch + gx] = addr(lp, hp);
+    }
+}
+
+// merge(L', a, b) -> Lab2BGR -> u8 (MagnifyCore.hpp:272-276)
+__global__ void __launch_bounds__(256) k_riesz_egress(const float* __restrict__ Lp, Level l, const int16_t* __restrict__ lab,
+                                                      int pitch16, size_t plane16, const float4* __restrict__ gtab,
+                                                      LabInvCoeffs coeffs, uint8_t* __restrict__ out, size_t step,
+                                                      size_t lane_stride, float* __restrict__ fout) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, lane = blockIdx.z;
+    if (x >= l.w) return;
+    const float L = Lp[(size_t)lane * l.plane + (size_t)y * l.pitch + x];
+    const int16_t* p = lab + (size_t)(lane * 3) * plane16 + (size_t)y * pitch16 + x;
+    const float A = fmaf((float)p[plane16], 1.0f / 64.0f, -128.0f);
+    const float B = fmaf((float)p[2 * plane16], 1.0f / 64.0f, -128.0f);
+    float ob, og, orr;
+    lab_to_bgr(L, A, B, coeffs, gtab, ob, og, orr);
+    uint8_t* q = out + (size_t)lane * lane_stride + (size_t)y * step + (size_t)x * 3;
+    q[0] = unit_to_u8(ob); q[1] = unit_to_u8(og); q[2] = unit_to_u8(orr);
+    if (fout) {
+        float* f = fout + (((size_t)lane * l.h + y) * l.w + x) * 3;
+        f[0] = ob; f[1] = og; f[2] = orr;
+    }
+}
+
+inline unsigned cdiv(int a, int b) { return (unsigned)((a + b - 1) / b); }
+
+}  // namespace
+
+void RieszMode::reset() {
+    arena.release();
+    lv.clear();
+    for (auto* v : {&oct, &cur_low, &cur_rx, &cur_ry, &old_low, &old_rx, &old_ry, &phase_c, &phase_s, &lo_r0c, &lo_r0s,
+                    &lo_r1c, &lo_r1s, &hi_r0c, &hi_r0s, &hi_r1c, &hi_r1s, &amp, &t_c, &t_s, &low_amp, &res})
+        v->clear();
+    lab16 = nullptr;
+    allocated = false;
+}
+
+#define KLAUNCH(name, level, ...)                                                  \
+    do {                                                                           \
+        const bool p__ = ctx.prof && ctx.prof->begin(name, level, ctx.stream);     \
+        __VA_ARGS__;                                                               \
+        if (p__) ctx.prof->end(ctx.stream);                                        \
+        MCK(cudaGetLastError());                                                   \
+        ++*ctx.launches;                                                           \
+    } while (0)
+
+mc_status RieszMode::build_pyramid(const ModeCtx& ctx) {
+    // RieszPyramid::buildPyramid (RieszPyramid.cpp:215-238); the Riesz pair itself is formed in the phase kernel
+    for (int i = 0; i < levels - 1; ++i) {
+        const Level& l = lv[(size_t)i];
+        dim3 grid(cdiv(l.w, RT_W), cdiv(l.h, RT_H), lanes);
+        KLAUNCH("riesz_analysis", i, k_riesz_analysis<<<grid, 256, 0, ctx.stream>>>(l, lv[(size_t)i + 1], oct[(size_t)i], cur_low[(size_t)i], oct[(size_t)i + 1]));
+    }
+    return MC_OK;
+}
+
+mc_status RieszMode::process(const ModeCtx& ctx, const FrameIO& io, const mc_params& p, int nlevels, int* produced) {
+    *produced = 0;
+    if (io.channels < 3) return MC_OK;  // MagnifyCore.hpp:212: gray input is a silent passthrough
+    const bool first = !allocated || std::isnan(loA[0]) || std::isnan(hiA[0]);  // :226
+    if (first) {
+        reset();
+        levels = nlevels; w = io.w; h = io.h;
+        lv.resize((size_t)levels);
+        int cw = w, ch = h;
+        for (int i = 0; i < levels; ++i) {
+            lv[(size_t)i] = make_level(cw, ch);
+            cw = cw / 2 + (cw % 2); ch = ch / 2 + (ch % 2);   // subsample(), RieszPyramid.cpp:262-263
+        }
+        auto alloc_set = [&](std::vector<float*>& v, int n_levels, bool zero) -> mc_status {
+            v.assign((size_t)levels, nullptr);
+            for (int i = 0; i < n_levels; ++i) {
+                const size_t n = (size_t)lanes * lv[(size_t)i].plane;
+                MCK(arena.alloc(&v[(size_t)i], n));
+                if (zero) MCK(cudaMemsetAsync(v[(size_t)i], 0, n * sizeof(float), ctx.stream));
+            }
+            return MC_OK;
+        };
+        mc_status st;
+        const int nb = levels - 1;  // band levels
+        if ((st = alloc_set(oct, levels, false)) != MC_OK) return st;
+        if ((st = alloc_set(cur_low, nb, false)) != MC_OK) return st;
+        for (auto* v : {&cur_rx, &cur_ry, &old_low, &amp, &t_c, &t_s, &low_amp})
+            if ((st = alloc_set(*v, nb, false)) != MC_OK) return st;
+        if ((st = alloc_set(res, levels, false)) != MC_OK) return st;
+        // init(): Riesz pair of `old`, phases and IIR registers start at zero (RieszPyramid.cpp:196-213, TemporalFilter.cpp:299-317)
+        for (auto* v : {&old_rx, &old_ry, &phase_c, &phase_s, &lo_r0c, &lo_r0s, &lo_r1c, &lo_r1s, &hi_r0c, &hi_r0s, &hi_r1c, &hi_r1s})
+            if ((st = alloc_set(*v, nb, true)) != MC_OK) return st;
+        pitch16 = round_up(w, 64);
+        plane16 = (size_t)h * pitch16;
+        void* lp = nullptr;
+        MCK(arena.alloc_bytes(&lp, (size_t)lanes * 3 * plane16 * sizeof(int16_t)));
+        lab16 = (int16_t*)lp;
+        lo_freq = p.coLow; hi_freq = p.coHigh; framerate = p.framerate;
+        auto design = [&](double f, double* A, double* B) {
+            const double wn = framerate == 0.0 ? 0.0 : f / (framerate / 2.0);  // TemporalFilter.cpp:324-327
+            std::vector<double> a, b;
+            butterworth(2, wn, a, b);
+            for (int k = 0; k < 3; ++k) { A[k] = a[(size_t)k]; B[k] = b[(size_t)k]; }
+        };
+        design(lo_freq, loA, loB);
+        design(hi_freq, hiA, hiB);
+        allocated = true;
+    }
+    // BGR -> Lab; only L is magnified (MagnifyCore.hpp:217-222)
+    LAUNCH("lab16", 0, launch_lab16(io, *ctx.tables, lab16, pitch16, plane16, ctx.stream));
+    {
+        dim3 grid(cdiv(w, 256), h, lanes);
+        KLAUNCH("L_plane", 0, k_s16_to_f32<<<grid, 256, 0, ctx.stream>>>(lab16, pitch16, plane16, 3, 100.0f / 16384.0f, 0.0f, lv[0], oct[0]));
+    }
+    mc_status st = build_pyramid(ctx);
+    if (st != MC_OK) return st;
+    if (first) {
+        // old = pyramid of the first frame with a zero Riesz pair; the frame itself is shown unmagnified (:239)
+        for (int i = 0; i < levels - 1; ++i) std::swap(cur_low[(size_t)i], old_low[(size_t)i]);
+        return MC_OK;
+    }
+    // cutoff changes re-design the filter, zero both filters' registers and rebuild `old` from this frame (:243-254)
+    bool rebuild_old = false;
+    auto zero_state = [&]() -> mc_status {
+        for (auto* v : {&phase_c, &phase_s, &lo_r0c, &lo_r0s, &lo_r1c, &lo_r1s, &hi_r0c, &hi_r0s, &hi_r1c, &hi_r1s})
+            for (int i = 0; i < levels - 1; ++i)
+                MCK(cudaMemsetAsync((*v)[(size_t)i], 0, (size_t)lanes * lv[(size_t)i].plane * sizeof(float), ctx.stream));
+        return MC_OK;
+    };
+    auto redesign = [&](double f, double* A, double* B) {
+        const double wn = framerate == 0.0 ? 0.0 : f / (framerate / 2.0);
+        std::vector<double> a, b;
+        butterworth(2, wn, a, b);
+        for (int k = 0; k < 3; ++k) { A[k] = a[(size_t)k]; B[k] = b[(size_t)k]; }
+    };
+    if (lo_freq != p.coLow) {
+        lo_freq = p.coLow;
+        redesign(lo_freq, loA, loB);
+        if ((st = zero_state()) != MC_OK) return st;
+        rebuild_old = true;
+    }
+    if (hi_freq != p.coHigh) {
+        hi_freq = p.coHigh;
+        redesign(hi_freq, hiA, hiB);
+        if ((st = zero_state()) != MC_OK) return st;
+        rebuild_old = true;
+    }
+    const int nb = levels - 1;
+    for (int i = 0; i < nb; ++i) {
+        PhaseArgs a;
+        a.l = lv[(size_t)i];
+        a.low = cur_low[(size_t)i];
+        a.plow = rebuild_old ? nullptr : old_low[(size_t)i];
+        a.prx = old_rx[(size_t)i]; a.pry = old_ry[(size_t)i];
+        a.rx = cur_rx[(size_t)i]; a.ry = cur_ry[(size_t)i];
+        a.ph_c = phase_c[(size_t)i]; a.ph_s = phase_s[(size_t)i];
+        a.lo_r0c = lo_r0c[(size_t)i]; a.lo_r0s = lo_r0s[(size_t)i]; a.lo_r1c = lo_r1c[(size_t)i]; a.lo_r1s = lo_r1s[(size_t)i];
+        a.hi_r0c = hi_r0c[(size_t)i]; a.hi_r0s = hi_r0s[(size_t)i]; a.hi_r1c = hi_r1c[(size_t)i]; a.hi_r1s = hi_r1s[(size_t)i];
+        a.amp = amp[(size_t)i]; a.t_c = t_c[(size_t)i]; a.t_s = t_s[(size_t)i];
+        a.lo = Butter{loB[0], loB[1], loB[2], loA[1], loA[2]};
+        a.hi = Butter{hiB[0], hiB[1], hiB[2], hiA[1], hiA[2]};
+        dim3 grid(cdiv(a.l.w, RT_W), cdiv(a.l.h, RT_H), lanes);
+        KLAUNCH("riesz_phase", i, k_riesz_phase<<<grid, 256, 0, ctx.stream>>>(a));
+    }
+    // *old = *cur (before amplification, :267): the buffers just written become `old`
+    for (int i = 0; i < nb; ++i) {
+        std::swap(cur_low[(size_t)i], old_low[(size_t)i]);
+        std::swap(cur_rx[(size_t)i], old_rx[(size_t)i]);
+        std::swap(cur_ry[(size_t)i], old_ry[(size_t)i]);
+    }
+    // amplify (RieszPyramid.cpp:248-252) — this frame's band/pair now live in the old_* buffers
+    const float alpha = (float)p.amplification;
+    const float thresh = (float)(p.coWavelength * (3.14159265358979323846 / 100.0));  // PI_PERCENT, :214,:269
+    for (int i = nb - 1; i >= 0; --i) {
+        AmpArgs a;
+        a.l = lv[(size_t)i];
+        a.amp = amp[(size_t)i]; a.t_c = t_c[(size_t)i]; a.t_s = t_s[(size_t)i];
+        a.low = old_low[(size_t)i]; a.rx = old_rx[(size_t)i]; a.ry = old_ry[(size_t)i];
+        a.out = low_amp[(size_t)i];
+        gaussian_kernel_13_3(a.g.k);
+        a.alpha = alpha; a.thresh = thresh;
+        dim3 grid(cdiv(a.l.w, RT_W), cdiv(a.l.h, RT_H), lanes);
+        KLAUNCH("riesz_amplify", i, k_riesz_amplify<<<grid, 256, 0, ctx.stream>>>(a));
+    }
+    // collapse (RieszPyramid.cpp:304-325)
+    const float* result = oct[(size_t)levels - 1];
+    for (int i = nb - 1; i >= 0; --i) {
+        const Level& l = lv[(size_t)i];
+        dim3 grid(cdiv(l.w, RT_W), cdiv(l.h, RT_H), lanes);
+        KLAUNCH("riesz_collapse", i, k_riesz_collapse<<<grid, 256, 0, ctx.stream>>>(l, lv[(size_t)i + 1], low_amp[(size_t)i], result, res[(size_t)i]));
+        result = res[(size_t)i];
+    }
+    {
+        dim3 grid(cdiv(w, 256), h, lanes);
+        KLAUNCH("riesz_egress", 0, k_riesz_egress<<<grid, 256, 0, ctx.stream>>>(result, lv[0], lab16, pitch16, plane16, ctx.tables->inv_gamma, ctx.tables->inv_coeffs, io.out, io.out_step, io.out_lane_stride, ctx.float_out));
+    }
+    *produced = 1;
+    return MC_OK;
+}
+
+void RieszMode::find_state(const char* name, int level, StateRef& out) {
+    out = StateRef{};
+    if (!allocated || level < 0 || level >= levels - 1) return;
+    struct { const char* n; std::vector<float*>* v; } map[] = {
+        {"old.lowpass", &old_low}, {"old.rx", &old_rx}, {"old.ry", &old_ry}, {"phase.c", &phase_c}, {"phase.s", &phase_s},
+        {"lo.r0.c", &lo_r0c}, {"lo.r0.s", &lo_r0s}, {"lo.r1.c", &lo_r1c}, {"lo.r1.s", &lo_r1s},
+        {"hi.r0.c", &hi_r0c}, {"hi.r0.s", &hi_r0s}, {"hi.r1.c", &hi_r1c}, {"hi.r1.s", &hi_r1s}};
+    for (auto& m : map)
+        if (!std::strcmp(name, m.n)) {
+            const Level& l = lv[(size_t)level];
+            out.ptr = (*m.v)[(size_t)level]; out.rows = l.h; out.cols = l.w; out.channels = 1; out.pitch = l.pitch; out.plane_stride = l.plane;
+            return;
+        }
+}
+
 }  // namespace mc

@@ -1,0 +1,126 @@
+"""Motion (Phase / Riesz) parity vs the oracle.
+
+Two tiers (SURVEY.md §A.7 — acos near 1 and the unbounded phase integrator make free-running parity
+chaotic for any implementation that is not bit-identical to OpenCV's 9x9 filter summation order):
+  tier 1  teacher-forced single step: oracle state of frame t-1 injected, frame t compared:
+          float output (BGR in [0,1], before quantisation) max-abs < 1e-4, u8 <= 1 LSB
+  tier 2  free-running over >= 32 frames: u8 <= 3 LSB, >= 99.5 % of samples identical,
+          p99.9 of the float error < 3e-3."""
+import numpy as np
+import pytest
+
+import lvm_b200 as L
+from lvm_b200.synth import synth_frame
+from oracle import livim_oracle as O
+from common import make_cfgs, u8_diff
+
+pytestmark = pytest.mark.gpu
+
+STATE = [("old.lowpass", lambda st, i: st.old.levels[i].lowpass), ("old.rx", lambda st, i: st.old.levels[i].rx),
+         ("old.ry", lambda st, i: st.old.levels[i].ry),
+         ("phase.c", lambda st, i: st.lo.phase[i][0]), ("phase.s", lambda st, i: st.lo.phase[i][1]),
+         ("lo.r0.c", lambda st, i: st.lo.reg0[i][0]), ("lo.r0.s", lambda st, i: st.lo.reg0[i][1]),
+         ("lo.r1.c", lambda st, i: st.lo.reg1[i][0]), ("lo.r1.s", lambda st, i: st.lo.reg1[i][1]),
+         ("hi.r0.c", lambda st, i: st.hi.reg0[i][0]), ("hi.r0.s", lambda st, i: st.hi.reg0[i][1]),
+         ("hi.r1.c", lambda st, i: st.hi.reg1[i][0]), ("hi.r1.s", lambda st, i: st.hi.reg1[i][1])]
+
+
+def inject(proc, ost, levels):
+    for i in range(levels - 1):
+        for name, get in STATE:
+            proc.set_state(name, i, np.ascontiguousarray(get(ost, i))[None, None])
+
+
+@pytest.mark.parametrize("w,h,levels", [(320, 240, 4), (250, 187, 3), (96, 64, 2)])
+def test_teacher_forced_single_step(w, h, levels):
+    cfg, ocfg = make_cfgs(O.MODE_PHASE, 50, 50.0, 0.4, 3.0, 0, levels)
+    proc, oproc = L.MagnificationProcessor(0), O.MagnificationProcessor()
+    proc.set_option("keep_float_output", 1)
+    worst = 0.0
+    for t in range(8):
+        f = synth_frame(t, w, h, 3)
+        if t >= 2:
+            inject(proc, oproc.riesz, levels)
+        dbg = {}
+        produced, out = proc.process_image(f, cfg)
+        oprod, oout = oproc.process(f, ocfg, dbg)
+        assert produced == oprod == (t >= 1)
+        if not produced:
+            continue
+        err = float(np.abs(proc.float_output(w, h, 3)[0] - dbg["output_bgr_f32"]).max())
+        worst = max(worst, err)
+        assert err < 1e-4, (t, err)
+        assert int(u8_diff(out, oout).max()) <= 1, t
+        # the updated state must track the oracle too.  Pyramid planes (Lab scale): 1e-4 absolute.  Phase
+        # accumulators / IIR registers: acos(1 - eps) ~ sqrt(2 eps) turns a 1e-7 relative difference of the
+        # 9x9 sums into up to ~5e-4 rad at isolated pixels, so max-abs < 1e-3 rad and p99.9 < 1e-4 rad.
+        for i in range(levels - 1):
+            for name, get in STATE:
+                e = np.abs(proc.get_state(name, i)[0, 0] - get(oproc.riesz, i))
+                if name.startswith("old."):
+                    assert float(e.max()) < 1e-4, (t, i, name, float(e.max()))
+                else:
+                    assert float(e.max()) < 1e-3 and float(np.quantile(e, 0.999)) < 1e-4, (t, i, name, float(e.max()))
+
+
+def test_free_running_32_frames():
+    w, h, levels = 320, 240, 4
+    cfg, ocfg = make_cfgs(O.MODE_PHASE, 50, 50.0, 0.4, 3.0, 0, levels)
+    proc, oproc = L.MagnificationProcessor(0), O.MagnificationProcessor()
+    proc.set_option("keep_float_output", 1)
+    for t in range(34):
+        f = synth_frame(t, w, h, 3)
+        dbg = {}
+        produced, out = proc.process_image(f, cfg)
+        oprod, oout = oproc.process(f, ocfg, dbg)
+        assert produced == oprod
+        if not produced:
+            continue
+        d8 = u8_diff(out, oout)
+        ferr = np.abs(proc.float_output(w, h, 3)[0] - dbg["output_bgr_f32"])
+        assert int(d8.max()) <= 3, (t, int(d8.max()))
+        assert float((d8 == 0).mean()) >= 0.995, (t, float((d8 == 0).mean()))
+        assert float(np.quantile(ferr, 0.999)) < 3e-3, t
+
+
+def test_gray_and_first_frame_passthrough():
+    proc = L.MagnificationProcessor(0)
+    cfg, _ = make_cfgs(O.MODE_PHASE, 50, 50.0, 0.4, 3.0, 0, 4)
+    g = synth_frame(0, 160, 120, 1)
+    for t in range(3):
+        produced, out = proc.process_image(g, cfg)       # gray input: silent passthrough (MagnifyCore.hpp:212)
+        assert not produced and out is g
+    f = synth_frame(0, 160, 120, 3)
+    produced, out = proc.process_image(f, cfg)           # channel change -> reset -> first frame passthrough
+    assert not produced and out is f
+    produced, out = proc.process_image(synth_frame(1, 160, 120, 3), cfg)
+    assert produced
+
+
+def test_cutoff_change_rebuilds_old_and_zeroes_filters():
+    w, h, levels = 200, 150, 3
+    proc, oproc = L.MagnificationProcessor(0), O.MagnificationProcessor()
+    seq = [(0.4, 3.0)] * 5 + [(0.8, 3.0)] * 4 + [(0.8, 2.0)] * 4
+    for t, (lo, hi) in enumerate(seq):
+        cfg, ocfg = make_cfgs(O.MODE_PHASE, 30, 50.0, lo, hi, 0, levels)
+        f = synth_frame(t, w, h, 3)
+        produced, out = proc.process_image(f, cfg)
+        oprod, oout = oproc.process(f, ocfg)
+        assert produced == oprod
+        if produced:
+            d8 = u8_diff(out, oout)
+            assert int(d8.max()) <= 3 and float((d8 == 0).mean()) >= 0.995, (t, int(d8.max()))
+
+
+def test_config3_1080p():
+    w, h, levels = 1920, 1080, 6
+    cfg, ocfg = make_cfgs(O.MODE_PHASE, 50, 50.0, 0.4, 3.0, 0, levels)
+    proc, oproc = L.MagnificationProcessor(0), O.MagnificationProcessor()
+    for t in range(4):
+        f = synth_frame(t, w, h, 3)
+        produced, out = proc.process_image(f, cfg)
+        oprod, oout = oproc.process(f, ocfg)
+        assert produced == oprod
+        if produced:
+            d8 = u8_diff(out, oout)
+            assert int(d8.max()) <= 3 and float((d8 == 0).mean()) >= 0.995, (t, int(d8.max()), float((d8 == 0).mean()))
