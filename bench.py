@@ -183,14 +183,13 @@ def run_ours(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     # one-time broadcast of the parameter block from rank 0 (the path's only collective)
-    p = capi.McParams()
+    from lvm_b200.shard import broadcast_params, max_over_ranks as _max_over_ranks
+    p = None
     if rank == 0:
+        p = capi.McParams()
         capi.lib().mc_params_from_ui(C.byref(p), capi.MODE_LAPLACE, UI["amplification"], UI["wavelength"], UI["low"],
                                      UI["high"], UI["chroma"], UI["levels"], UI["fps"])
-    blob = torch.frombuffer(bytearray(bytes(p)), dtype=torch.uint8).cuda()
-    if dist:
-        dist.broadcast(blob, src=0)
-        C.memmove(C.byref(p), bytes(blob.cpu().numpy().tobytes()), C.sizeof(p))
+    p = broadcast_params(p, dist, device="cuda")
 
     lanes, T = args.lanes, args.clip_frames
     clip_h = make_clip(T, lanes)
@@ -216,11 +215,7 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.synchronize()
 
     def max_over_ranks(x):
-        if not dist:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return _max_over_ranks(x, dist, device="cuda")
 
     # ---- device-resident throughput ----------------------------------------------------------
     for i in range(args.warmup):
