@@ -180,6 +180,7 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         import torch.distributed as dist_
         dist = dist_
+        os.environ.setdefault("NCCL_DEBUG", "WARN")   # keep stdout to the single JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     # one-time broadcast of the parameter block from rank 0 (the path's only collective)
@@ -233,7 +234,8 @@ def run_ours(args, rank, world, local_rank):
     e1.record(stream)
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1))
-    launches = proc.launch_count - l0
+    from lvm_b200.shard import sum_over_ranks
+    launches = int(sum_over_ranks(float(proc.launch_count - l0), dist, device="cuda"))
     clocks = sampler.stop() if rank == 0 else None
     fps = world * lanes * args.steps / (ms * 1e-3)
 

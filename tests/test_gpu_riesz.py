@@ -52,15 +52,18 @@ def test_teacher_forced_single_step(w, h, levels):
         assert err < 1e-4, (t, err)
         assert int(u8_diff(out, oout).max()) <= 1, t
         # the updated state must track the oracle too.  Pyramid planes (Lab scale): 1e-4 absolute.  Phase
-        # accumulators / IIR registers: acos(1 - eps) ~ sqrt(2 eps) turns a 1e-7 relative difference of the
-        # 9x9 sums into up to ~5e-4 rad at isolated pixels, so max-abs < 1e-3 rad and p99.9 < 1e-4 rad.
+        # accumulators / IIR registers: p99.9 < 1e-4 rad.  Isolated pixels may jump: the reference's arcCos
+        # returns +-1.0 *radians* when q_r/|q| rounds 1 ulp outside [-1, 1] (RieszPyramid.cpp:15-18),
+        # and acos(1 - eps) ~ sqrt(2 eps), so a last-bit difference in the 9x9 sums can move one pixel's
+        # phase by up to 1 rad; such pixels are bounded in number (<= 1e-4 of the plane), not in size.
         for i in range(levels - 1):
             for name, get in STATE:
                 e = np.abs(proc.get_state(name, i)[0, 0] - get(oproc.riesz, i))
                 if name.startswith("old."):
                     assert float(e.max()) < 1e-4, (t, i, name, float(e.max()))
                 else:
-                    assert float(e.max()) < 1e-3 and float(np.quantile(e, 0.999)) < 1e-4, (t, i, name, float(e.max()))
+                    assert float(np.quantile(e, 0.999)) < 1e-4 and float((e > 1e-3).mean()) <= 1e-4, \
+                        (t, i, name, float(e.max()), float(np.quantile(e, 0.999)), float((e > 1e-3).mean()))
 
 
 def test_free_running_32_frames():
