@@ -172,3 +172,12 @@ def test_pipelined_submit_collect_matches_blocking():
         done += 1
     for t in range(n):
         assert np.array_equal(outs[t], ref[t]), t
+
+
+def test_cpp_adapter_runs_on_gpu():
+    """The reference-side C++ IProcessor adapter (built against stub reference headers) magnifies a frame."""
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.abspath(__file__)), "adapter_stub", "adapter_check")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "OK gpu" in r.stdout, (r.returncode, r.stdout, r.stderr)

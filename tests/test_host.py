@@ -136,3 +136,19 @@ def test_gaussian_taps(hc):
     t = np.empty(13, np.float32)
     hc.hc_gauss13(t.ctypes.data_as(C.c_void_p))
     assert np.array_equal(t, cv2.getGaussianKernel(13, 3.0, cv2.CV_32F).ravel())
+
+
+def test_cpp_adapter_compiles_and_refuses_without_gpu(built):
+    """adapter/MagnificationProcessorB200.hpp (the reference-side IProcessor) builds against stub reference
+    headers; with no GPU its constructor must throw (rc 3) — there is no CPU fallback."""
+    import subprocess
+    import torch
+    exe = os.path.join(ROOT, "tests", "adapter_stub", "adapter_check")
+    if not os.path.exists(exe):
+        import __graft_entry__ as g
+        g.build()
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    if torch.cuda.is_available():
+        assert r.returncode == 0 and "OK gpu" in r.stdout, r.stdout
+    else:
+        assert r.returncode == 3 and "no usable CUDA device" in r.stdout, r.stdout
