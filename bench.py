@@ -285,9 +285,12 @@ def run_ours(args, rank, world, local_rank):
             if name == "level" and lvl >= 1:
                 alg = 16 * CH * px[lvl] * lanes                       # two f32 state planes, read + write
                 io = alg + 4 * CH * (px[lvl] + px[lvl] + px[lvl + 1]) * lanes  # + G_l read, M_l write, G_{l+1} write
-            elif name == "level":                                     # level 0: Lab16 -> pyrDown -> G1
+            elif name in ("level", "down"):                           # level 0: Lab16 -> pyrDown -> G1
                 alg = 0
                 io = (2 * CH * px[0] + 4 * CH * px[1]) * lanes
+            elif name == "ingest_lab":                                # u8 -> Lab16 planes + G1
+                alg = CH * px[0] * lanes
+                io = alg + 2 * CH * px[0] * lanes + 4 * CH * px[1] * lanes
             elif name == "lab16":
                 alg = CH * px[0] * lanes                              # u8 frame read
                 io = alg + 2 * CH * px[0] * lanes                     # + Lab16 write

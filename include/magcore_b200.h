@@ -135,7 +135,9 @@ void* mc_stream(mc_handle* h);
  *        only to compare level-0 state planes with the oracle.
  *   "pipeline_depth"  (default 3)
  *   "keep_float_output" (default 0): keep the pre-quantisation float image (tests)
- *   "profile_kernels" (default 0): see mc_profile_read */
+ *   "profile_kernels" (default 0): see mc_profile_read
+ *   "use_tma" (default 1): stage the fused level kernel's tiles with TMA (cp.async.bulk.tensor); 0 selects
+ *        the 128-bit LDG staging path (same results; kept for A/B measurements) */
 mc_status mc_set_option(mc_handle* h, const char* key, int value);
 
 /* Test-only access to temporal state planes as dense f32 [lanes][channels][rows][cols].

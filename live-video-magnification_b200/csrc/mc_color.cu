@@ -293,7 +293,7 @@ mc_status ColorMode::process(const ModeCtx& ctx, const FrameIO& io, const mc_par
         a.in_kind = 0; a.g = G[(size_t)l]; a.in_plane = lv[(size_t)l].plane; a.in_row = lv[(size_t)l].pitch;
         a.channels = C; a.lf = lv[(size_t)l]; a.lc = lv[(size_t)l + 1]; a.g_next = G[(size_t)l + 1];
         a.planes = planes; a.band = 0;
-        LAUNCH("gauss_down", l, launch_level(a, ctx.stream));
+        LAUNCH("gauss_down", l, launch_down(a, ctx.stream));
     }
     // append to the rolling window; once full drop the oldest column (SpatialFilter.cpp:63-84)
     const Level& ls = lv[(size_t)levels];

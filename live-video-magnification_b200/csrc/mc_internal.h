@@ -58,6 +58,10 @@ struct FrameIO {
 cudaError_t launch_lab16(const FrameIO& io, const DeviceTables& tb, int16_t* lab, int pitch16, size_t plane16,
                          cudaStream_t s);
 
+// fused ingest of the production path: u8 BGR -> Lab16 planes + G1 = pyrDown(Lab) (MagnifyCore.hpp:87-96, level 0)
+cudaError_t launch_ingest_lab(const FrameIO& io, const DeviceTables& tb, int16_t* lab, int pitch16, size_t plane16,
+                              float* g1, const Level& l1, cudaStream_t s);
+
 struct LevelArgs {
     int in_kind = 0;           // 0: f32 planes, 1: Lab int16 planes, 2: u8 gray frame
     const void* g = nullptr;   // input planes of this level (fine)
@@ -74,10 +78,16 @@ struct LevelArgs {
     int band = 1;              // 0: only pyrDown (the level-0 band never reaches the output)
     double c_hi = 0, one_minus_c_hi = 0, c_lo = 0, one_minus_c_lo = 0;
     float gain = 0;
+    const void* tmap = nullptr;   // CUtensorMap of the f32 input planes (TMA-staged tile) or null
 };
+// 128-byte opaque CUtensorMap storage + encoder for the level kernel's (72 x 39 x 1) box
+struct alignas(64) TensorMapStorage { unsigned char bytes[128]; };
+bool make_level_tensor_map(void* out_map, const float* base, const Level& l, int planes);
 // fused per level: pyrDown + pyrUp + subtract + dual-EMA update + gain (SpatialFilter.cpp:25-38,
 // TemporalFilter.cpp:9-22, MagnifyCore.hpp:127-134)
 cudaError_t launch_level(const LevelArgs& a, cudaStream_t s);
+// pure pyrDown of `a.g` into `a.g_next` (register/shuffle strip kernel; used when a.band == 0)
+cudaError_t launch_down(const LevelArgs& a, cudaStream_t s);
 
 // cur_l = pyrUp(cur_{l+1}) + m_l, in place in m_l (SpatialFilter.cpp:52-61)
 cudaError_t launch_collapse(const Level& lf, const Level& lc, float* m_fine, const float* m_coarse, int planes,

@@ -11,11 +11,38 @@
 // (+halo) in shared memory with 128-bit loads, runs the separable 5-tap passes out of that tile, and
 // each thread owns a 4x2 pixel block so state planes move as 128-bit coalesced vectors.  Tiles that
 // touch an image border take a generic (slower) path that applies OpenCV's border rules.
+#include <cuda.h>   // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
+
 #include "mc_internal.h"
 
 namespace mc {
 
 namespace {
+
+// ---- TMA (cp.async.bulk.tensor) + mbarrier primitives -------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");   // make the init visible to the async proxy
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "MC_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra MC_DONE_%=;\n\t"
+        "bra MC_WAIT_%=;\n\t"
+        "MC_DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 3-D tiled load {x, y, plane} -> shared; out-of-bounds elements are zero-filled by the TMA unit
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, int x, int y, int z, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z) : "memory");
+}
 
 constexpr float kInv256 = 1.0f / 256.0f;
 constexpr float kInv64 = 1.0f / 64.0f;
@@ -31,6 +58,9 @@ __device__ __forceinline__ float down5(float a, float b, float c, float d, float
 __global__ void __launch_bounds__(256) k_lab16(const uint8_t* __restrict__ in, size_t in_step, size_t in_lane_stride,
                                                int w, int h, const LabLutEntry* __restrict__ lut,
                                                int16_t* __restrict__ lab, int pitch16, size_t plane16, int aligned) {
+    __shared__ uint16_t s_tx[256];   // u8 sample -> (LUT cell << 8 | 4-bit weight), see lab_tx_of_u8
+    s_tx[threadIdx.x] = (uint16_t)lab_tx_of_u8(threadIdx.x);
+    __syncthreads();
     const int lane = blockIdx.z;
     const int y = blockIdx.y;
     const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
@@ -54,7 +84,7 @@ __global__ void __launch_bounds__(256) k_lab16(const uint8_t* __restrict__ in, s
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         int sL, sA, sB;
-        bgr_u8_to_lab_fixed(px[3 * i], px[3 * i + 1], px[3 * i + 2], lut, sL, sA, sB);
+        lab_fixed_from_tx(s_tx[px[3 * i]], s_tx[px[3 * i + 1]], s_tx[px[3 * i + 2]], lut, sL, sA, sB);
         L[i] = (short)sL; A[i] = (short)sA; B[i] = (short)sB;
     }
     int16_t* o = lab + (size_t)(lane * 3) * plane16 + (size_t)y * pitch16 + x;  // pitch16 % 64 == 0, x % 4 == 0
@@ -125,11 +155,12 @@ struct LevelKArgs {
     int in_vec_ok;            // u8 rows are 4-byte aligned
 };
 
-template <int KIND>
-__global__ void __launch_bounds__(256) k_level(const LevelKArgs a) {
-    __shared__ __align__(16) float sG[GH][GW];
+template <int KIND, bool USE_TMA>
+__global__ void __launch_bounds__(256) k_level(const LevelKArgs a, const __grid_constant__ CUtensorMap tmap) {
+    __shared__ __align__(128) float sG[GH][GW];
     __shared__ __align__(16) float sH[GH][DP];
     __shared__ __align__(16) float sD[DH][DP];
+    __shared__ __align__(8) uint64_t tma_bar;
     const int plane = blockIdx.z;
     const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
     const int wf = a.lf.w, hf = a.lf.h, wc = a.lc.w, hc = a.lc.h;
@@ -139,7 +170,41 @@ __global__ void __launch_bounds__(256) k_level(const LevelKArgs a) {
     if (KIND == IN_F32) base = reinterpret_cast<const float*>(a.g) + (size_t)plane * a.in_plane;
     else if (KIND == IN_LAB16) base = reinterpret_cast<const short*>(a.g) + (size_t)plane * a.in_plane;
     else base = reinterpret_cast<const uint8_t*>(a.g) + (size_t)plane * a.in_plane;
-    load_fine_window<KIND>(sG, base, a.in_row, wf, hf, x0, y0, interior, a.sc[ch], a.of[ch]);
+    if (USE_TMA) {
+        // The (GH x GW) window of this plane is fetched by ONE bulk-tensor copy issued by one thread; the
+        // TMA unit zero-fills whatever lies outside the level, and border tiles then patch those cells with
+        // BORDER_REFLECT_101 copies taken from inside the window.
+        if (threadIdx.x == 0) mbar_init(&tma_bar, 1);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(&tma_bar, GH * GW * sizeof(float));
+            tma_load_3d(&sG[0][0], &tmap, x0 - 4, y0 - 4, plane, &tma_bar);
+        }
+        mbar_wait(&tma_bar, 0);
+        if (!interior) {
+            __syncthreads();
+            float fix[(GH * GW + 255) / 256];
+            int n = 0;
+            for (int i = threadIdx.x; i < GH * GW; i += 256, ++n) {
+                const int r = i / GW, c = i - r * GW;
+                const int gy = y0 - 4 + r, gx = x0 - 4 + c;
+                int rr = reflect101(gy, hf) - (y0 - 4), cc = reflect101(gx, wf) - (x0 - 4);
+                rr = rr < 0 ? 0 : (rr > GH - 1 ? GH - 1 : rr);
+                cc = cc < 0 ? 0 : (cc > GW - 1 ? GW - 1 : cc);
+                fix[n] = sG[rr][cc];
+            }
+            __syncthreads();
+            n = 0;
+            for (int i = threadIdx.x; i < GH * GW; i += 256, ++n) {
+                const int r = i / GW, c = i - r * GW;
+                sG[r][c] = fix[n];
+            }
+        }
+    } else {
+        const float scv = ch == 0 ? a.sc[0] : (ch == 1 ? a.sc[1] : a.sc[2]);
+        const float ofv = ch == 0 ? a.of[0] : (ch == 1 ? a.of[1] : a.of[2]);
+        load_fine_window<KIND>(sG, base, a.in_row, wf, hf, x0, y0, interior, scv, ofv);
+    }
     __syncthreads();
 
     // pyrDown row pass: sH[r][j] for the coarse columns of the window (pairs of columns per item)
@@ -250,6 +315,241 @@ __global__ void __launch_bounds__(256) k_level(const LevelKArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// down_strip: pure cv::pyrDown (level 0 of the production path, Gaussian chain of Color) with the row
+// pass in registers + warp shuffles and the column pass as a register sliding window — no shared
+// memory, no per-pixel index arithmetic.  One warp = a strip of 128 fine columns (lane = 4 fine
+// columns = 2 coarse columns); lanes 0 and 31 only provide the halo, so strips advance by 120 columns
+// and no lane ever needs a divergent extra load.  Each warp walks DS_ROWS coarse rows top to bottom,
+// loading four fine rows ahead of their use.
+// ------------------------------------------------------------------------------------------------
+constexpr int DS_ROWS = 16;   // coarse rows per warp
+constexpr int DS_WARPS = 4;   // warps per CTA (consecutive row chunks of the same strip)
+constexpr int DS_COLS = 120;  // fine columns produced per strip (lanes 1..30)
+
+struct DsRaw { float v0, v1, v2, v3; };   // one fine row as seen by one lane (before the row pass)
+struct DsRow { float h0, h1; };
+
+template <int KIND>
+__device__ __forceinline__ DsRaw ds_load(const void* base, size_t row_off, int gx, int wf, bool fast, float sc, float of) {
+    DsRaw r;
+    if (fast) {
+        if (KIND == IN_F32) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + row_off + gx));
+            r.v0 = t.x; r.v1 = t.y; r.v2 = t.z; r.v3 = t.w;
+        } else if (KIND == IN_LAB16) {
+            const short4 t = __ldg(reinterpret_cast<const short4*>(reinterpret_cast<const short*>(base) + row_off + gx));
+            r.v0 = fmaf((float)t.x, sc, of); r.v1 = fmaf((float)t.y, sc, of); r.v2 = fmaf((float)t.z, sc, of); r.v3 = fmaf((float)t.w, sc, of);
+        } else {
+            const uchar4 t = __ldg(reinterpret_cast<const uchar4*>(reinterpret_cast<const uint8_t*>(base) + row_off + gx));
+            r.v0 = (float)t.x * sc; r.v1 = (float)t.y * sc; r.v2 = (float)t.z * sc; r.v3 = (float)t.w * sc;
+        }
+    } else {   // columns outside [0, wf): BORDER_REFLECT_101
+        r.v0 = load_scalar<KIND>(base, row_off + reflect101(gx, wf), sc, of);
+        r.v1 = load_scalar<KIND>(base, row_off + reflect101(gx + 1, wf), sc, of);
+        r.v2 = load_scalar<KIND>(base, row_off + reflect101(gx + 2, wf), sc, of);
+        r.v3 = load_scalar<KIND>(base, row_off + reflect101(gx + 3, wf), sc, of);
+    }
+    return r;
+}
+
+// Row pass of cv::pyrDown: the two left / one right neighbour values come from the adjacent lanes.
+__device__ __forceinline__ DsRow ds_rowpass(const DsRaw& r) {
+    const float a0 = __shfl_up_sync(0xffffffffu, r.v2, 1), a1 = __shfl_up_sync(0xffffffffu, r.v3, 1);
+    const float b0 = __shfl_down_sync(0xffffffffu, r.v0, 1);
+    DsRow o;
+    o.h0 = down5(a0, a1, r.v0, r.v1, r.v2);
+    o.h1 = down5(r.v0, r.v1, r.v2, r.v3, b0);
+    return o;
+}
+
+struct DownArgs {
+    const void* g; size_t in_plane; int in_row; int channels;
+    float sc[3], of[3];
+    Level lf, lc;
+    float* g_next;
+    int in_vec_ok;
+};
+
+template <int KIND>
+__global__ void __launch_bounds__(32 * DS_WARPS) k_down_strip(const DownArgs a) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int plane = blockIdx.z;
+    const int wf = a.lf.w, hf = a.lf.h, wc = a.lc.w, hc = a.lc.h;
+    const int gx = blockIdx.x * DS_COLS - 4 + lane * 4;               // first fine column of this lane (multiple of 4)
+    const int k0 = (blockIdx.y * DS_WARPS + warp) * DS_ROWS;          // first coarse row of this warp
+    if (k0 >= hc) return;
+    const int ch = plane % a.channels;
+    const float sc = ch == 0 ? a.sc[0] : (ch == 1 ? a.sc[1] : a.sc[2]);   // no dynamic indexing of the param struct
+    const float of = ch == 0 ? a.of[0] : (ch == 1 ? a.of[1] : a.of[2]);
+    const void* base;
+    if (KIND == IN_F32) base = reinterpret_cast<const float*>(a.g) + (size_t)plane * a.in_plane;
+    else if (KIND == IN_LAB16) base = reinterpret_cast<const short*>(a.g) + (size_t)plane * a.in_plane;
+    else base = reinterpret_cast<const uint8_t*>(a.g) + (size_t)plane * a.in_plane;
+    const bool fast = gx >= 0 && (gx + 4 <= wf) && a.in_vec_ok;       // whole vector inside the row
+    float* __restrict__ out = a.g_next + (size_t)plane * a.lc.plane;
+    const int jx = gx >> 1;                                           // first coarse column of this lane
+    const bool writer = lane >= 1 && lane <= 30 && jx < wc;
+    const int k_end = min(k0 + DS_ROWS, hc);
+
+    // p1..p4 / q1..q4 = row-pass results of fine rows 2k-2 .. 2k+1 for the lane's two coarse columns.
+    // Four fine rows are loaded per iteration before any of them is consumed (memory-level parallelism),
+    // producing two coarse rows.
+#define DS_LOAD(row) ds_load<KIND>(base, (size_t)reflect101((row), hf) * a.in_row, gx, wf, fast, sc, of)
+    float p1, p2, p3, p4, q1, q2, q3, q4;
+    {
+        const DsRaw a1 = DS_LOAD(2 * k0 - 2), a2 = DS_LOAD(2 * k0 - 1), a3 = DS_LOAD(2 * k0), a4 = DS_LOAD(2 * k0 + 1);
+        const DsRow r1 = ds_rowpass(a1), r2 = ds_rowpass(a2), r3 = ds_rowpass(a3), r4 = ds_rowpass(a4);
+        p1 = r1.h0; q1 = r1.h1; p2 = r2.h0; q2 = r2.h1; p3 = r3.h0; q3 = r3.h1; p4 = r4.h0; q4 = r4.h1;
+    }
+    for (int k = k0; k < k_end; k += 2) {
+        const DsRaw ra = DS_LOAD(2 * k + 2), rb = DS_LOAD(2 * k + 3), rc = DS_LOAD(2 * k + 4), rd = DS_LOAD(2 * k + 5);
+        const DsRow ha = ds_rowpass(ra), hb = ds_rowpass(rb), hc_ = ds_rowpass(rc), hd = ds_rowpass(rd);
+        if (writer) {
+            const float d0 = down5(p1, p2, p3, p4, ha.h0) * kInv256, d1 = down5(q1, q2, q3, q4, ha.h1) * kInv256;
+            float* q = out + (size_t)k * a.lc.pitch + jx;
+            if (jx + 1 < wc) *reinterpret_cast<float2*>(q) = make_float2(d0, d1);
+            else q[0] = d0;
+            if (k + 1 < k_end) {
+                const float e0 = down5(p3, p4, ha.h0, hb.h0, hc_.h0) * kInv256, e1 = down5(q3, q4, ha.h1, hb.h1, hc_.h1) * kInv256;
+                q += a.lc.pitch;
+                if (jx + 1 < wc) *reinterpret_cast<float2*>(q) = make_float2(e0, e1);
+                else q[0] = e0;
+            }
+        }
+        p1 = ha.h0; p2 = hb.h0; p3 = hc_.h0; p4 = hd.h0;
+        q1 = ha.h1; q2 = hb.h1; q3 = hc_.h1; q4 = hd.h1;
+    }
+#undef DS_LOAD
+}
+
+// ------------------------------------------------------------------------------------------------
+// ingest_lab: u8 BGR -> Lab (exact OpenCV LUT) -> { Lab16 planes for egress, G1 = pyrDown(Lab) } in one
+// pass.  Same strip structure as down_strip (row pass by shuffles, column pass as a register window),
+// with the three Lab channels carried together; the LUT gathers (L1-bound) hide the stencil math.
+// ------------------------------------------------------------------------------------------------
+constexpr int IG_ROWS = 32;   // coarse rows per warp (halo rows re-convert 4 of 68 fine rows)
+constexpr int IG_WARPS = 4;
+
+struct IngestArgs {
+    const uint8_t* in; size_t in_step, in_lane_stride;
+    int w, h, aligned;
+    const LabLutEntry* lut;
+    int16_t* lab; int pitch16; size_t plane16;
+    float* g1; Level l1;
+};
+
+struct Lab4 { float L[4], A[4], B[4]; };
+
+__device__ __forceinline__ void ig_row(const IngestArgs& a, const uint16_t* s_tx, const uint8_t* frame, int row, int gx,
+                                       bool fast, bool own, int16_t* lab_lane, float (&hL)[2], float (&hA)[2],
+                                       float (&hB)[2]) {
+    // loads 4 BGR pixels of fine row `row` (reflected), converts, optionally stores Lab16, returns the row pass
+    const int ry = reflect101(row, a.h);
+    const uint8_t* p = frame + (size_t)ry * a.in_step;
+    uint32_t px[12];
+    if (fast) {
+        const uint32_t* q = reinterpret_cast<const uint32_t*>(p + (size_t)gx * 3);
+        const uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            px[i] = (w0 >> (8 * i)) & 0xff;
+            px[4 + i] = (w1 >> (8 * i)) & 0xff;
+            px[8 + i] = (w2 >> (8 * i)) & 0xff;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint8_t* q = p + (size_t)reflect101(gx + i, a.w) * 3;
+            px[3 * i] = __ldg(q); px[3 * i + 1] = __ldg(q + 1); px[3 * i + 2] = __ldg(q + 2);
+        }
+    }
+    int sL[4], sA[4], sB[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        lab_fixed_from_tx(s_tx[px[3 * i]], s_tx[px[3 * i + 1]], s_tx[px[3 * i + 2]], a.lut, sL[i], sA[i], sB[i]);
+    if (own) {   // this warp owns the row and the lane owns the columns: emit the Lab16 planes
+        int16_t* o = lab_lane + (size_t)row * a.pitch16 + gx;
+        *reinterpret_cast<short4*>(o) = make_short4((short)sL[0], (short)sL[1], (short)sL[2], (short)sL[3]);
+        *reinterpret_cast<short4*>(o + a.plane16) = make_short4((short)sA[0], (short)sA[1], (short)sA[2], (short)sA[3]);
+        *reinterpret_cast<short4*>(o + 2 * a.plane16) = make_short4((short)sB[0], (short)sB[1], (short)sB[2], (short)sB[3]);
+    }
+    DsRaw r;
+    DsRow o;
+    r.v0 = (float)sL[0] * (100.0f / 16384.0f); r.v1 = (float)sL[1] * (100.0f / 16384.0f);
+    r.v2 = (float)sL[2] * (100.0f / 16384.0f); r.v3 = (float)sL[3] * (100.0f / 16384.0f);
+    o = ds_rowpass(r); hL[0] = o.h0; hL[1] = o.h1;
+    r.v0 = fmaf((float)sA[0], 1.0f / 64.0f, -128.0f); r.v1 = fmaf((float)sA[1], 1.0f / 64.0f, -128.0f);
+    r.v2 = fmaf((float)sA[2], 1.0f / 64.0f, -128.0f); r.v3 = fmaf((float)sA[3], 1.0f / 64.0f, -128.0f);
+    o = ds_rowpass(r); hA[0] = o.h0; hA[1] = o.h1;
+    r.v0 = fmaf((float)sB[0], 1.0f / 64.0f, -128.0f); r.v1 = fmaf((float)sB[1], 1.0f / 64.0f, -128.0f);
+    r.v2 = fmaf((float)sB[2], 1.0f / 64.0f, -128.0f); r.v3 = fmaf((float)sB[3], 1.0f / 64.0f, -128.0f);
+    o = ds_rowpass(r); hB[0] = o.h0; hB[1] = o.h1;
+}
+
+__global__ void __launch_bounds__(32 * IG_WARPS) k_ingest_lab(const IngestArgs a) {
+    __shared__ uint16_t s_tx[256];
+    for (int i = threadIdx.x; i < 256; i += 32 * IG_WARPS) s_tx[i] = (uint16_t)lab_tx_of_u8(i);
+    __syncthreads();
+    const int lane_id = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = blockIdx.z;                                       // stream
+    const int gx = blockIdx.x * DS_COLS - 4 + lane_id * 4;
+    const int k0 = (blockIdx.y * IG_WARPS + warp) * IG_ROWS;
+    const int wc = a.l1.w, hc = a.l1.h;
+    if (k0 >= hc) return;
+    const int k_end = min(k0 + IG_ROWS, hc);
+    const uint8_t* frame = a.in + (size_t)lane * a.in_lane_stride;
+    int16_t* lab_lane = a.lab + (size_t)(lane * 3) * a.plane16;
+    const bool fast = gx >= 0 && gx + 4 <= a.w && a.aligned;
+    const bool col_owner = lane_id >= 1 && lane_id <= 30 && gx < a.w;
+    const int jx = gx >> 1;
+    const bool writer = lane_id >= 1 && lane_id <= 30 && jx < wc;
+    float* __restrict__ oL = a.g1 + (size_t)(lane * 3) * a.l1.plane;
+
+    // window[c][i] = row pass of fine row (2k-2+i), channel c, for the lane's two coarse columns
+    float wL[4][2], wA[4][2], wB[4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int row = 2 * k0 - 2 + i;
+        ig_row(a, s_tx, frame, row, gx, fast, col_owner && row >= 2 * k0 && row < a.h, lab_lane, wL[i], wA[i], wB[i]);
+    }
+    for (int k = k0; k < k_end; ++k) {
+        float nL[2], nA[2], nB[2];
+        {
+            const int row = 2 * k + 2;
+            ig_row(a, s_tx, frame, row, gx, fast, col_owner && row < 2 * k_end && row < a.h, lab_lane, nL, nA, nB);
+        }
+        if (writer) {
+            float* q = oL + (size_t)k * a.l1.pitch + jx;
+            const bool two = jx + 1 < wc;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                float (*wnd)[2] = c == 0 ? wL : (c == 1 ? wA : wB);
+                const float* nn = c == 0 ? nL : (c == 1 ? nA : nB);
+                const float d0 = down5(wnd[0][0], wnd[1][0], wnd[2][0], wnd[3][0], nn[0]) * kInv256;
+                const float d1 = down5(wnd[0][1], wnd[1][1], wnd[2][1], wnd[3][1], nn[1]) * kInv256;
+                float* qc = q + (size_t)c * a.l1.plane;
+                if (two) *reinterpret_cast<float2*>(qc) = make_float2(d0, d1);
+                else qc[0] = d0;
+            }
+        }
+        // slide by two fine rows: rows 2k .. 2k+3 become the next window
+        float mL[2], mA[2], mB[2];
+        {
+            const int row = 2 * k + 3;
+            const bool need = k + 1 < k_end;   // the last iteration's extra row is never used
+            if (need) ig_row(a, s_tx, frame, row, gx, fast, col_owner && row < 2 * k_end && row < a.h, lab_lane, mL, mA, mB);
+            else { mL[0] = mL[1] = mA[0] = mA[1] = mB[0] = mB[1] = 0.f; }
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            wL[0][j] = wL[2][j]; wL[1][j] = wL[3][j]; wL[2][j] = nL[j]; wL[3][j] = mL[j];
+            wA[0][j] = wA[2][j]; wA[1][j] = wA[3][j]; wA[2][j] = nA[j]; wA[3][j] = mA[j];
+            wB[0][j] = wB[2][j]; wB[1][j] = wB[3][j]; wB[2][j] = nB[j]; wB[3][j] = mB[j];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // collapse (small levels): cur_l = pyrUp(cur_{l+1}) + m_l, in place in m_l.  Tile 64 x 16.
 // ------------------------------------------------------------------------------------------------
 constexpr int CW = 64, CH_ = 16;
@@ -316,34 +616,39 @@ __global__ void __launch_bounds__(256) k_egress(const EgressArgs a) {
     const int w1 = a.l1.w, h1 = a.l1.h;
     if (a.m1) {
         if (a.c2) {
-            for (int i = threadIdx.x; i < C * E2H * E2W; i += 256) {
-                const int ch = i / (E2H * E2W), rem = i - ch * (E2H * E2W);
-                const int k = rem / E2W, j = rem - k * E2W;
+            // level-2 window (border rule of pyrUp pre-applied); one position per thread, channels inside
+            for (int i = threadIdx.x; i < E2H * E2W; i += 256) {
+                const int k = i / E2W, j = i - k * E2W;
                 const int iy = upsrc(y0 / 4 - 2 + k, a.l2.h), ix = upsrc(x0 / 4 - 2 + j, a.l2.w);
-                sC2[ch][k][j] = __ldg(a.c2 + (size_t)(lane * C + ch) * a.l2.plane + (size_t)iy * a.l2.pitch + ix);
+                const float* p2 = a.c2 + (size_t)(lane * C) * a.l2.plane + (size_t)iy * a.l2.pitch + ix;
+#pragma unroll
+                for (int ch = 0; ch < C; ++ch) sC2[ch][k][j] = __ldg(p2 + (size_t)ch * a.l2.plane);
             }
             __syncthreads();
         }
         // level-1 window: position (k, j) <-> level-1 pixel upsrc(y0/2-1+k), upsrc(x0/2-1+j)
-        for (int i = threadIdx.x; i < C * DH * DW; i += 256) {
-            const int ch = i / (DH * DW), rem = i - ch * (DH * DW);
-            const int k = rem / DW, j = rem - k * DW;
+        for (int i = threadIdx.x; i < DH * DW; i += 256) {
+            const int k = i / DW, j = i - k * DW;
             const int y1 = upsrc(y0 / 2 - 1 + k, h1), x1 = upsrc(x0 / 2 - 1 + j, w1);
-            float v = __ldg(a.m1 + (size_t)(lane * C + ch) * a.l1.plane + (size_t)y1 * a.l1.pitch + x1);
-            if (a.c2) {
-                // pyrUp of level 2 at (y1, x1): window index of level-2 pixel i is i - (x0/4 - 2); the
-                // border rule was applied when the window was loaded (entries hold s[upsrc(i)]).
-                const int jx = (x1 >> 1) - (x0 / 4 - 2), ky = (y1 >> 1) - (y0 / 4 - 2);
-                float r[3];
+            const float* p1 = a.m1 + (size_t)(lane * C) * a.l1.plane + (size_t)y1 * a.l1.pitch + x1;
+            // pyrUp of level 2 at (y1, x1): window index of level-2 pixel i is i - (x0/4 - 2); the border
+            // rule was applied when the window was loaded (entries hold s[upsrc(i)]).
+            const int jx = (x1 >> 1) - (x0 / 4 - 2), ky = (y1 >> 1) - (y0 / 4 - 2);
 #pragma unroll
-                for (int q = 0; q < 3; ++q) {
-                    const float* row = sC2[ch][ky - 1 + q];
-                    r[q] = (x1 & 1) ? (row[jx] + row[jx + 1]) * 4.0f : (row[jx - 1] + row[jx] * 6.0f + row[jx + 1]);
+            for (int ch = 0; ch < C; ++ch) {
+                float v = __ldg(p1 + (size_t)ch * a.l1.plane);
+                if (a.c2) {
+                    float r[3];
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) {
+                        const float* row = sC2[ch][ky - 1 + q];
+                        r[q] = (x1 & 1) ? (row[jx] + row[jx + 1]) * 4.0f : (row[jx - 1] + row[jx] * 6.0f + row[jx + 1]);
+                    }
+                    const float up = (y1 & 1) ? ((r[1] + r[2]) * 4.0f) * kInv64 : (r[0] + r[1] * 6.0f + r[2]) * kInv64;
+                    v = up + v;
                 }
-                const float up = (y1 & 1) ? ((r[1] + r[2]) * 4.0f) * kInv64 : (r[0] + r[1] * 6.0f + r[2]) * kInv64;
-                v = up + v;
+                sD[ch][k][j] = v;
             }
-            sD[ch][k][j] = v;
         }
         __syncthreads();
     }
@@ -397,7 +702,9 @@ __global__ void __launch_bounds__(256) k_egress(const EgressArgs a) {
                 float ob, og, orr;
                 lab_to_bgr(L, A, B, a.coeffs, a.gtab, ob, og, orr);
                 of[3 * i] = ob; of[3 * i + 1] = og; of[3 * i + 2] = orr;
-                o8[3 * i] = unit_to_u8(ob); o8[3 * i + 1] = unit_to_u8(og); o8[3 * i + 2] = unit_to_u8(orr);
+                // lab_to_bgr clips to [0,1] before the gamma spline, so the saturating branches of
+                // convertTo reduce to a min with 255 (NaN -> 0 by the conversion itself)
+                o8[3 * i] = unit01_to_u8(ob); o8[3 * i + 1] = unit01_to_u8(og); o8[3 * i + 2] = unit01_to_u8(orr);
             }
         } else {
             const uint8_t* p = a.in + (size_t)lane * a.in_lane_stride + (size_t)gy * a.in_step + gx;
@@ -439,11 +746,49 @@ inline unsigned cdiv(int a, int b) { return (unsigned)((a + b - 1) / b); }
 
 }  // namespace
 
+// Encodes a 3-D tiled tensor map {w, h, planes} over pitched f32 planes with the level kernel's box.
+// cuTensorMapEncodeTiled is resolved through the runtime so the library needs no link-time libcuda.
+bool make_level_tensor_map(void* out_map, const float* base, const Level& l, int planes) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
+            cudaGetLastError();
+            return false;
+        }
+        encode = reinterpret_cast<EncodeFn>(fn);
+    }
+    const cuuint64_t dims[3] = {(cuuint64_t)l.w, (cuuint64_t)l.h, (cuuint64_t)planes};
+    const cuuint64_t strides[2] = {(cuuint64_t)l.pitch * sizeof(float), (cuuint64_t)l.plane * sizeof(float)};
+    const cuuint32_t box[3] = {(cuuint32_t)GW, (cuuint32_t)GH, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    const CUresult r = encode(reinterpret_cast<CUtensorMap*>(out_map), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base),
+                              dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
 cudaError_t launch_lab16(const FrameIO& io, const DeviceTables& tb, int16_t* lab, int pitch16, size_t plane16,
                          cudaStream_t s) {
     const int aligned = (reinterpret_cast<uintptr_t>(io.in) % 4 == 0) && (io.in_step % 4 == 0) && (io.in_lane_stride % 4 == 0);
     dim3 grid(cdiv(cdiv(io.w, 4), 256), io.h, io.lanes);
     k_lab16<<<grid, 256, 0, s>>>(io.in, io.in_step, io.in_lane_stride, io.w, io.h, tb.lab_lut, lab, pitch16, plane16, aligned);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_ingest_lab(const FrameIO& io, const DeviceTables& tb, int16_t* lab, int pitch16, size_t plane16,
+                              float* g1, const Level& l1, cudaStream_t s) {
+    IngestArgs a;
+    a.in = io.in; a.in_step = io.in_step; a.in_lane_stride = io.in_lane_stride;
+    a.w = io.w; a.h = io.h;
+    a.aligned = (reinterpret_cast<uintptr_t>(io.in) % 4 == 0) && (io.in_step % 4 == 0) && (io.in_lane_stride % 4 == 0);
+    a.lut = tb.lab_lut; a.lab = lab; a.pitch16 = pitch16; a.plane16 = plane16; a.g1 = g1; a.l1 = l1;
+    dim3 grid(cdiv(io.w, DS_COLS), cdiv(l1.h, IG_ROWS * IG_WARPS), io.lanes);
+    k_ingest_lab<<<grid, 32 * IG_WARPS, 0, s>>>(a);
     return cudaGetLastError();
 }
 
@@ -457,9 +802,24 @@ cudaError_t launch_level(const LevelArgs& a, cudaStream_t s) {
     k.gain = a.gain;
     k.in_vec_ok = a.in_kind == IN_U8 ? ((reinterpret_cast<uintptr_t>(a.g) % 4 == 0) && (a.in_row % 4 == 0) && (a.in_plane % 4 == 0)) : 1;
     dim3 grid(cdiv(a.lf.w, TW), cdiv(a.lf.h, TH), a.planes);
-    if (a.in_kind == IN_F32) k_level<IN_F32><<<grid, 256, 0, s>>>(k);
-    else if (a.in_kind == IN_LAB16) k_level<IN_LAB16><<<grid, 256, 0, s>>>(k);
-    else k_level<IN_U8><<<grid, 256, 0, s>>>(k);
+    static const CUtensorMap dummy{};
+    if (a.in_kind == IN_F32 && a.tmap) k_level<IN_F32, true><<<grid, 256, 0, s>>>(k, *reinterpret_cast<const CUtensorMap*>(a.tmap));
+    else if (a.in_kind == IN_F32) k_level<IN_F32, false><<<grid, 256, 0, s>>>(k, dummy);
+    else if (a.in_kind == IN_LAB16) k_level<IN_LAB16, false><<<grid, 256, 0, s>>>(k, dummy);
+    else k_level<IN_U8, false><<<grid, 256, 0, s>>>(k, dummy);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_down(const LevelArgs& a, cudaStream_t s) {
+    DownArgs k;
+    k.g = a.g; k.in_plane = a.in_plane; k.in_row = a.in_row; k.channels = a.channels;
+    for (int i = 0; i < 3; ++i) { k.sc[i] = a.sc[i]; k.of[i] = a.of[i]; }
+    k.lf = a.lf; k.lc = a.lc; k.g_next = a.g_next;
+    k.in_vec_ok = a.in_kind == IN_U8 ? ((reinterpret_cast<uintptr_t>(a.g) % 4 == 0) && (a.in_row % 4 == 0) && (a.in_plane % 4 == 0)) : 1;
+    dim3 grid(cdiv(a.lf.w, DS_COLS), cdiv(a.lc.h, DS_ROWS * DS_WARPS), a.planes);
+    if (a.in_kind == IN_F32) k_down_strip<IN_F32><<<grid, 32 * DS_WARPS, 0, s>>>(k);
+    else if (a.in_kind == IN_LAB16) k_down_strip<IN_LAB16><<<grid, 32 * DS_WARPS, 0, s>>>(k);
+    else k_down_strip<IN_U8><<<grid, 32 * DS_WARPS, 0, s>>>(k);
     return cudaGetLastError();
 }
 

@@ -16,8 +16,9 @@ namespace mc {
 constexpr int kLabLutDim = 33;          // OpenCV LAB_LUT_DIM
 constexpr int kGammaTabSize = 1024;     // OpenCV GAMMA_TAB_SIZE
 
-// One packed LUT entry: Lab int16 triples of lattice points (b,g,r) and (b,g,r+1).
-struct alignas(16) LabLutEntry { int16_t v[8]; };  // {L0,a0,b0,L1,a1,b1,0,0}
+// One packed LUT entry: Lab int16 values of lattice points (b,g,r) [index 0] and (b,g,r+1) [index 1],
+// interleaved per channel so that one dp2a does the r-interpolation of a channel.
+struct alignas(16) LabLutEntry { int16_t v[8]; };  // {L0,L1,a0,a1,b0,b1,0,0}
 
 MC_HD int reflect101(int i, int n) {
     if (i < 0) i = -i;
@@ -45,6 +46,16 @@ MC_HD uint8_t unit_to_u8(float x) {
     return (uint8_t)(int)v;
 }
 
+// same for x known to lie in [0, 1+eps] (or NaN): round-half-even, NaN -> 0, min with 255
+MC_HD uint8_t unit01_to_u8(float x) {
+#if defined(__CUDA_ARCH__)
+    const int v = __float2int_rn(fmaf(x, 255.0f, 0.003921568859368563f));
+    return (uint8_t)min(max(v, 0), 255);
+#else
+    return unit_to_u8(x);
+#endif
+}
+
 // generic convertTo(CV_8U, alpha, beta) used by Color egress (MagnifyCore.hpp:202-203)
 MC_HD uint8_t scaled_to_u8(float x, float a, float b) {
     float v = rintf(fmaf(x, a, b));
@@ -57,47 +68,53 @@ MC_HD uint8_t scaled_to_u8(float x, float a, float b) {
 #define MC_LDG16(p) __ldg(reinterpret_cast<const int4*>(p))
 #endif
 
+// Per-channel quantisation of a u8 sample as OpenCV's float path sees it: cx = round(v*(1/255)*2^14),
+// LUT cell t = cx >> 9 and 4-bit weight x = (cx >> 5) & 15.  Returned packed as (t << 8) | x.
+MC_HD int lab_tx_of_u8(int v) {
+    const float c = ((float)v * 0.003921568859368563f) * 16384.0f;
+#if defined(__CUDA_ARCH__)
+    const int cx = __float2int_rn(c);
+#else
+    const int cx = (int)lrintf(c);
+#endif
+    return ((cx >> 9) << 8) | ((cx >> 5) & 15);
+}
+
 // cv::cvtColor(COLOR_BGR2Lab) on CV_32F input that came from u8/255 — bit-exact restatement of
 // OpenCV's 33^3 int16 LUT + 4-bit fixed-point trilinear interpolation.
-// lut is [b][g][r] packed entries.  Fixed-point result: L*2^14/100, (a+128)*64, (b+128)*64.
-MC_HD void bgr_u8_to_lab_fixed(uint8_t b8, uint8_t g8, uint8_t r8, const LabLutEntry* __restrict__ lut,
-                               int& sL, int& sA, int& sB) {
-#if defined(__CUDA_ARCH__)
-    const int cb = __float2int_rn(u8_to_unit(b8) * 16384.0f);
-    const int cg = __float2int_rn(u8_to_unit(g8) * 16384.0f);
-    const int cr = __float2int_rn(u8_to_unit(r8) * 16384.0f);
-#else
-    const int cb = (int)lrintf(u8_to_unit(b8) * 16384.0f);
-    const int cg = (int)lrintf(u8_to_unit(g8) * 16384.0f);
-    const int cr = (int)lrintf(u8_to_unit(r8) * 16384.0f);
-#endif
-    const int tb = cb >> 9, tg = cg >> 9, tr = cr >> 9;
-    const int xb = (cb >> 5) & 15, xg = (cg >> 5) & 15, xr = (cr >> 5) & 15;
+// lut is [b][g][r] packed entries; txb/txg/txr are lab_tx_of_u8() of the three samples (the kernels read
+// them from a 256-entry shared-memory table).  Fixed-point result: L*2^14/100, (a+128)*64, (b+128)*64.
+MC_HD void lab_fixed_from_tx(int txb, int txg, int txr, const LabLutEntry* __restrict__ lut, int& sL, int& sA, int& sB) {
+    const int tb = txb >> 8, tg = txg >> 8, tr = txr >> 8;
+    const int xb = txb & 15, xg = txg & 15, xr = txr & 15;
     const int tb1 = tb + 1 > 32 ? 32 : tb + 1, tg1 = tg + 1 > 32 ? 32 : tg + 1;
-    sL = 0; sA = 0; sB = 0;
-#pragma unroll
-    for (int db = 0; db < 2; ++db) {
-#pragma unroll
-        for (int dg = 0; dg < 2; ++dg) {
-            const int ib = db ? tb1 : tb, ig = dg ? tg1 : tg;
-            const int wbg = (db ? xb : 16 - xb) * (dg ? xg : 16 - xg);
-            const LabLutEntry* e = lut + ((ib * kLabLutDim + ig) * kLabLutDim + tr);
+    const LabLutEntry* e00 = lut + ((tb * kLabLutDim + tg) * kLabLutDim + tr);
+    const int dg = (tg1 - tg) * kLabLutDim, db = (tb1 - tb) * kLabLutDim * kLabLutDim;
+    const int w00 = (16 - xb) * (16 - xg), w01 = (16 - xb) * xg, w10 = xb * (16 - xg), w11 = xb * xg;
 #if defined(__CUDA_ARCH__)
-            const int4 q = MC_LDG16(e);
-            const int L0 = (int)(short)(q.x & 0xffff), a0 = q.x >> 16;
-            const int b0 = (int)(short)(q.y & 0xffff), L1 = q.y >> 16;
-            const int a1 = (int)(short)(q.z & 0xffff), b1 = q.z >> 16;
+    const int wr = (16 - xr) | (xr << 8);                       // int8 pair for dp2a: lo * (16-x) + hi * x
+    const int4 q00 = MC_LDG16(e00), q01 = MC_LDG16(e00 + dg), q10 = MC_LDG16(e00 + db), q11 = MC_LDG16(e00 + db + dg);
+    sL = w00 * __dp2a_lo(q00.x, wr, 0) + w01 * __dp2a_lo(q01.x, wr, 0) + w10 * __dp2a_lo(q10.x, wr, 0) + w11 * __dp2a_lo(q11.x, wr, 0);
+    sA = w00 * __dp2a_lo(q00.y, wr, 0) + w01 * __dp2a_lo(q01.y, wr, 0) + w10 * __dp2a_lo(q10.y, wr, 0) + w11 * __dp2a_lo(q11.y, wr, 0);
+    sB = w00 * __dp2a_lo(q00.z, wr, 0) + w01 * __dp2a_lo(q01.z, wr, 0) + w10 * __dp2a_lo(q10.z, wr, 0) + w11 * __dp2a_lo(q11.z, wr, 0);
 #else
-            const int L0 = e->v[0], a0 = e->v[1], b0 = e->v[2], L1 = e->v[3], a1 = e->v[4], b1 = e->v[5];
-#endif
-            sL += wbg * ((16 - xr) * L0 + xr * L1);
-            sA += wbg * ((16 - xr) * a0 + xr * a1);
-            sB += wbg * ((16 - xr) * b0 + xr * b1);
-        }
+    const LabLutEntry* es[4] = {e00, e00 + dg, e00 + db, e00 + db + dg};
+    const int ws[4] = {w00, w01, w10, w11};
+    sL = sA = sB = 0;
+    for (int i = 0; i < 4; ++i) {
+        sL += ws[i] * ((16 - xr) * es[i]->v[0] + xr * es[i]->v[1]);
+        sA += ws[i] * ((16 - xr) * es[i]->v[2] + xr * es[i]->v[3]);
+        sB += ws[i] * ((16 - xr) * es[i]->v[4] + xr * es[i]->v[5]);
     }
+#endif
     sL = (sL + 2048) >> 12;
     sA = (sA + 2048) >> 12;
     sB = (sB + 2048) >> 12;
+}
+
+MC_HD void bgr_u8_to_lab_fixed(uint8_t b8, uint8_t g8, uint8_t r8, const LabLutEntry* __restrict__ lut,
+                               int& sL, int& sA, int& sB) {
+    lab_fixed_from_tx(lab_tx_of_u8(b8), lab_tx_of_u8(g8), lab_tx_of_u8(r8), lut, sL, sA, sB);
 }
 
 // Float Lab as OpenCV returns it: L in [0,100], a,b in [-128,128).
@@ -127,6 +144,17 @@ MC_HD float spline_gamma(float v, const float4* __restrict__ tab) {
     return ((t.w * fr + t.z) * fr + t.y) * fr + t.x;
 }
 
+// Inverse sRGB transfer as OpenCV evaluates it.  OpenCV's 1024-segment spline only departs from the
+// analytic curve in its first 8 segments (up to 7.8e-5 at the knee v = 0.0031; < 2e-7 for v >= 8/1024), so
+// there the device evaluates 1.055 v^(1/2.4) - 0.055 with two SFU ops instead of a table gather, and keeps the
+// spline itself for the dark end where the difference matters.
+MC_HD float inv_gamma(float v, const float4* __restrict__ tab) {
+#if defined(__CUDA_ARCH__)
+    if (v >= 8.0f / 1024.0f) return fmaf(1.055f, exp2f(__log2f(v) * (1.0f / 2.4f)), -0.055f);
+#endif
+    return spline_gamma(v, tab);
+}
+
 // cv::cvtColor(COLOR_Lab2BGR) on CV_32F (analytic inverse + spline-interpolated sRGB gamma,
 // output clipped to [0,1]); restated from OpenCV's Lab2RGBfloat, checked against cv2 to ~1e-5.
 MC_HD void lab_to_bgr(float L, float a, float b, const LabInvCoeffs& k, const float4* __restrict__ gtab,
@@ -152,9 +180,9 @@ MC_HD void lab_to_bgr(float L, float a, float b, const LabInvCoeffs& k, const fl
     vb = fminf(fmaxf(vb, 0.0f), 1.0f);
     vg = fminf(fmaxf(vg, 0.0f), 1.0f);
     vr = fminf(fmaxf(vr, 0.0f), 1.0f);
-    ob = spline_gamma(vb, gtab);
-    og = spline_gamma(vg, gtab);
-    orr = spline_gamma(vr, gtab);
+    ob = inv_gamma(vb, gtab);
+    og = inv_gamma(vg, gtab);
+    orr = inv_gamma(vr, gtab);
 }
 
 // iirFilter (TemporalFilter.cpp:9-22): cv::addWeighted rounds once from a double sum.

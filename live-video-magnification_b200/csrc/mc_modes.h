@@ -34,6 +34,7 @@ struct ModeCtx {
     bool faithful0;
     float* float_out;  // optional [lanes][h][w][C] pre-quantisation tap
     Profiler* prof;    // optional
+    bool use_tma;      // stage level-kernel tiles with cp.async.bulk.tensor (option "use_tma", default on)
 };
 
 // Launch bookkeeping shared by the mode drivers: counts the launch, optionally brackets it with events.
@@ -83,6 +84,9 @@ struct MotionMode {
     int pitch16 = 0;
     size_t plane16 = 0;
     DeviceArena arena;
+
+    std::vector<TensorMapStorage> tmaps;   // per level: TMA descriptor of G[l] (tmap_valid[l] != 0)
+    std::vector<char> tmap_valid;
 
     void reset();
     mc_status process(const ModeCtx& ctx, const FrameIO& io, const mc_params& p, int levels, int* produced);

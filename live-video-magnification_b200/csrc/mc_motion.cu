@@ -58,6 +58,11 @@ mc_status MotionMode::allocate(const ModeCtx& ctx, const FrameIO& io, int nlevel
         }
         if (live) MCK(arena.alloc(&M[(size_t)l], n));
     }
+    // TMA descriptors for the f32 inputs of the fused level kernels
+    tmaps.assign((size_t)levels + 1, TensorMapStorage{});
+    tmap_valid.assign((size_t)levels + 1, 0);
+    for (int l = 1; l < levels; ++l)
+        tmap_valid[(size_t)l] = make_level_tensor_map(&tmaps[(size_t)l], G[(size_t)l], lv[(size_t)l], (int)planes) ? 1 : 0;
     if (channels == 3) {
         pitch16 = round_up(w, 64);
         plane16 = (size_t)h * pitch16;
@@ -83,10 +88,13 @@ mc_status MotionMode::process(const ModeCtx& ctx, const FrameIO& io, const mc_pa
     if (c_lo == 0) c_lo = 0.01;  // TemporalFilter.cpp:11-12
 
     // ingest: u8 BGR -> Lab16 planes (gray frames are read directly by the level-0 kernel)
-    if (channels == 3) LAUNCH("lab16", 0, launch_lab16(io, *ctx.tables, lab16, pitch16, plane16, ctx.stream));
+    // (production path, >= 2 levels: one fused kernel also builds G1; otherwise Lab16 alone)
+    const bool fused_ingest = channels == 3 && !faithful && levels >= 2;
+    if (fused_ingest) LAUNCH("ingest_lab", 0, launch_ingest_lab(io, *ctx.tables, lab16, pitch16, plane16, G[1], lv[1], ctx.stream));
+    else if (channels == 3) LAUNCH("lab16", 0, launch_lab16(io, *ctx.tables, lab16, pitch16, plane16, ctx.stream));
 
     // analysis: one fused kernel per level (level 0 only builds G1 unless the faithful option is on)
-    const int l_begin = (levels >= 2 || faithful) ? 0 : levels;
+    const int l_begin = fused_ingest ? 1 : ((levels >= 2 || faithful) ? 0 : levels);
     for (int l = l_begin; l < levels; ++l) {
         LevelArgs a;
         if (l == 0) {
@@ -100,6 +108,7 @@ mc_status MotionMode::process(const ModeCtx& ctx, const FrameIO& io, const mc_pa
             }
         } else {
             a.in_kind = 0; a.g = G[(size_t)l]; a.in_plane = lv[(size_t)l].plane; a.in_row = lv[(size_t)l].pitch;
+            if (tmap_valid[(size_t)l] && ctx.use_tma) a.tmap = &tmaps[(size_t)l];
         }
         a.channels = channels;
         a.lf = lv[(size_t)l]; a.lc = lv[(size_t)l + 1];
@@ -111,7 +120,8 @@ mc_status MotionMode::process(const ModeCtx& ctx, const FrameIO& io, const mc_pa
         a.band = (l >= 1 || faithful) ? 1 : 0;
         a.c_hi = c_hi; a.one_minus_c_hi = 1 - c_hi; a.c_lo = c_lo; a.one_minus_c_lo = 1 - c_lo;
         a.gain = gains[(size_t)l];
-        LAUNCH("level", l, launch_level(a, ctx.stream));
+        if (a.band) LAUNCH("level", l, launch_level(a, ctx.stream));
+        else LAUNCH("down", l, launch_down(a, ctx.stream));
     }
     if (first && faithful)  // st.lowpassHi/Lo[levels] = residual (MagnifyCore.hpp:100-101)
     {

@@ -32,8 +32,9 @@ void build_lab_lut_packed(std::vector<LabLutEntry>& out) {
                 const int16_t* e0 = &raw[(((size_t)b * n + g) * n + r) * 3];
                 const int16_t* e1 = &raw[(((size_t)b * n + g) * n + r1) * 3];
                 LabLutEntry& e = out[((size_t)b * n + g) * n + r];
-                e.v[0] = e0[0]; e.v[1] = e0[1]; e.v[2] = e0[2];
-                e.v[3] = e1[0]; e.v[4] = e1[1]; e.v[5] = e1[2];
+                e.v[0] = e0[0]; e.v[1] = e1[0];   // L at r, r+1
+                e.v[2] = e0[1]; e.v[3] = e1[1];   // a
+                e.v[4] = e0[2]; e.v[5] = e1[2];   // b
                 e.v[6] = 0; e.v[7] = 0;
             }
 }

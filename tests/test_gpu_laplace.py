@@ -181,3 +181,20 @@ def test_cpp_adapter_runs_on_gpu():
     exe = os.path.join(os.path.dirname(os.path.abspath(__file__)), "adapter_stub", "adapter_check")
     r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and "OK gpu" in r.stdout, (r.returncode, r.stdout, r.stderr)
+
+
+def test_tma_staging_equals_ldg_staging():
+    """The fused level kernel stages its tiles with TMA (cp.async.bulk.tensor, zero-filled borders patched to
+    REFLECT_101 in shared memory); option use_tma=0 selects the 128-bit LDG path.  Results must be identical,
+    also for sizes whose border tiles are ragged."""
+    for (w, h, c, lv) in [(640, 480, 3, 4), (333, 251, 1, 5), (1920, 1080, 3, 6)]:
+        cfg, _ = make_cfgs(O.MODE_LAPLACE, 20, 50.0, 0.4, 3.0, 30, lv)
+        a, b = L.MagnificationProcessor(0), L.MagnificationProcessor(0)
+        b.set_option("use_tma", 0)
+        for t in range(4):
+            f = synth_frame(t, w, h, c)
+            _, oa = a.process_image(f, cfg)
+            _, ob = b.process_image(f, cfg)
+            assert np.array_equal(oa, ob), (w, h, t)
+        for lvl in range(1, lv):
+            assert np.array_equal(a.get_state("lowpassHi", lvl), b.get_state("lowpassHi", lvl))
