@@ -60,36 +60,73 @@ __global__ void k_s16_to_f32(const int16_t* __restrict__ src, int pitch16, size_
     dst[(size_t)lane * l.plane + (size_t)y * l.pitch + x] = fmaf(v, scale, off);
 }
 
+// 9x9 kernels are register-blocked: a thread owns a 1x4 strip, loads 12 tile values per kernel row with three
+// 128-bit shared-memory reads and issues 36 FMAs on them.  Rows are dealt to warps so that both rows of a
+// warp have the same parity (the sub-sampled low-pass / the zero-injected up-sampling only touch one parity),
+// which keeps every parity branch warp-uniform.
+constexpr int R9_W = 64, R9_H = 16;                  // output tile
+constexpr int R9_SW = R9_W + 8, R9_SH = R9_H + 8;    // + 4 halo
+
+__device__ __forceinline__ int r9_row(int tid) {     // tile row of this thread: warp w -> rows {b, b+2}, b = 4(w>>1) + (w&1)
+    const int w = tid >> 5, half = (tid >> 4) & 1;
+    return 4 * (w >> 1) + (w & 1) + 2 * half;
+}
+
+__device__ __forceinline__ void r9_load_tile(float (*s)[R9_SW], const float* __restrict__ src, const Level& l, int x0, int y0) {
+    const bool interior = x0 >= 4 && x0 + R9_W + 4 <= l.w && y0 >= 4 && y0 + R9_H + 4 <= l.h;
+    if (interior) {
+        for (int i = threadIdx.x; i < R9_SH * (R9_SW / 4); i += 256) {
+            const int r = i / (R9_SW / 4), c4 = i - r * (R9_SW / 4);
+            *reinterpret_cast<float4*>(&s[r][4 * c4]) =
+                __ldg(reinterpret_cast<const float4*>(src + (size_t)(y0 - 4 + r) * l.pitch + (x0 - 4 + 4 * c4)));
+        }
+    } else {
+        for (int i = threadIdx.x; i < R9_SH * R9_SW; i += 256) {
+            const int r = i / R9_SW, c = i - r * R9_SW;
+            s[r][c] = __ldg(src + (size_t)reflect101(y0 - 4 + r, l.h) * l.pitch + reflect101(x0 - 4 + c, l.w));
+        }
+    }
+}
+
 // hp = filter2D(oct, HP) ; next = subsample(filter2D(oct, 2*LP))   (REFLECT_101, correlation)
 __global__ void __launch_bounds__(256) k_riesz_analysis(Level l, Level ln, const float* __restrict__ oct,
                                                         float* __restrict__ hp, float* __restrict__ next) {
-    __shared__ float s[RA_H][RA_W + 1];
+    __shared__ __align__(16) float s[R9_SH][R9_SW];
     const int plane = blockIdx.z;
-    const int x0 = blockIdx.x * RT_W, y0 = blockIdx.y * RT_H;
-    const float* __restrict__ src = oct + (size_t)plane * l.plane;
-    for (int i = threadIdx.x; i < RA_H * RA_W; i += 256) {
-        const int r = i / RA_W, c = i - r * RA_W;
-        s[r][c] = __ldg(src + (size_t)reflect101(y0 - 4 + r, l.h) * l.pitch + reflect101(x0 - 4 + c, l.w));
-    }
+    const int x0 = blockIdx.x * R9_W, y0 = blockIdx.y * R9_H;
+    r9_load_tile(s, oct + (size_t)plane * l.plane, l, x0, y0);
     __syncthreads();
-    for (int i = threadIdx.x; i < RT_H * RT_W; i += 256) {
-        const int y = i / RT_W, x = i - y * RT_W;
-        const int gy = y0 + y, gx = x0 + x;
-        if (gy >= l.h || gx >= l.w) continue;
-        float acc = 0.f;
+    const int tx = threadIdx.x & 15, y = r9_row(threadIdx.x);
+    const int gy = y0 + y, gx = x0 + 4 * tx;
+    if (gy >= l.h || gx >= l.w) return;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f}, lp0 = 0.f, lp1 = 0.f;
+    const bool even_row = next != nullptr && !(gy & 1);   // warp-uniform
 #pragma unroll
-        for (int ky = 0; ky < 9; ++ky)
+    for (int ky = 0; ky < 9; ++ky) {
+        const float4 a0 = *reinterpret_cast<const float4*>(&s[y + ky][4 * tx]);
+        const float4 a1 = *reinterpret_cast<const float4*>(&s[y + ky][4 * tx + 4]);
+        const float4 a2 = *reinterpret_cast<const float4*>(&s[y + ky][4 * tx + 8]);
+        const float v[12] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x, a2.y, a2.z, a2.w};
 #pragma unroll
-            for (int kx = 0; kx < 9; ++kx) acc = fmaf(c_hp[ky * 9 + kx], s[y + ky][x + kx], acc);
-        hp[(size_t)plane * l.plane + (size_t)gy * l.pitch + gx] = acc;
-        if (next && !(gy & 1) && !(gx & 1)) {
-            float a2 = 0.f;
+        for (int kx = 0; kx < 9; ++kx) {
+            const float c = c_hp[ky * 9 + kx];
 #pragma unroll
-            for (int ky = 0; ky < 9; ++ky)
-#pragma unroll
-                for (int kx = 0; kx < 9; ++kx) a2 = fmaf(2.0f * c_lp[ky * 9 + kx], s[y + ky][x + kx], a2);
-            next[(size_t)plane * ln.plane + (size_t)(gy >> 1) * ln.pitch + (gx >> 1)] = a2;
+            for (int p = 0; p < 4; ++p) acc[p] = fmaf(c, v[p + kx], acc[p]);
         }
+        if (even_row) {
+#pragma unroll
+            for (int kx = 0; kx < 9; ++kx) {
+                const float c = 2.0f * c_lp[ky * 9 + kx];
+                lp0 = fmaf(c, v[kx], lp0);
+                lp1 = fmaf(c, v[2 + kx], lp1);
+            }
+        }
+    }
+    float* o = hp + (size_t)plane * l.plane + (size_t)gy * l.pitch + gx;
+    *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1], acc[2], acc[3]);   // rows are padded to 32 floats
+    if (even_row) {
+        float* q = next + (size_t)plane * ln.plane + (size_t)(gy >> 1) * ln.pitch + (gx >> 1);
+        *reinterpret_cast<float2*>(q) = make_float2(lp0, lp1);                        // gx/2 is even -> 8-byte aligned; padded row
     }
 }
 
@@ -255,35 +292,72 @@ __global__ void __launch_bounds__(256) k_riesz_amplify(const AmpArgs a) {
 }
 
 // result_i = filter2D(injectZerosEven(nearest_up(result_{i+1})), 2*LP) + filter2D(band_i, HP)
+// The zero-injected image is never materialised: only the taps that land on even/even fine positions are
+// evaluated (25/20/20/16 of 81, by output parity), reading the coarse samples straight from shared memory.
+constexpr int RC_CW = R9_SW / 2, RC_CH = R9_SH / 2;   // even fine positions of the window: 36 x 12
+
+template <int PAR>   // PAR = parity of the output row
+__device__ __forceinline__ void rc_lowpass(const float (*sc)[RC_CW], int y, int tx, float (&lp)[4]) {
+    // output (y, x): taps ky = PAR, PAR+2, ... on coarse row (y + ky) / 2 ; kx likewise by column parity
+#pragma unroll
+    for (int i = 0; i < 5 - PAR; ++i) {
+        const int ky = 2 * i + PAR;
+        const float* row = sc[(y + ky) >> 1];
+        const float2 q0 = *reinterpret_cast<const float2*>(&row[2 * tx]);
+        const float2 q1 = *reinterpret_cast<const float2*>(&row[2 * tx + 2]);
+        const float2 q2 = *reinterpret_cast<const float2*>(&row[2 * tx + 4]);
+        const float v[6] = {q0.x, q0.y, q1.x, q1.y, q2.x, q2.y};   // coarse columns x/2 .. x/2+5 (x = 4 tx)
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {                               // even outputs x, x+2: kx = 0,2,4,6,8
+            const float c = 2.0f * c_lp[ky * 9 + 2 * j];
+            lp[0] = fmaf(c, v[j], lp[0]);
+            lp[2] = fmaf(c, v[j + 1], lp[2]);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {                               // odd outputs x+1, x+3: kx = 1,3,5,7
+            const float c = 2.0f * c_lp[ky * 9 + 2 * j + 1];
+            lp[1] = fmaf(c, v[j + 1], lp[1]);
+            lp[3] = fmaf(c, v[j + 2], lp[3]);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) k_riesz_collapse(Level l, Level lc, const float* __restrict__ band,
                                                         const float* __restrict__ coarse, float* __restrict__ out) {
-    __shared__ float sb[RA_H][RA_W + 1];
-    __shared__ float su[RA_H][RA_W + 1];
+    __shared__ __align__(16) float sb[R9_SH][R9_SW];
+    __shared__ __align__(16) float sc[RC_CH][RC_CW];
     const int plane = blockIdx.z;
-    const int x0 = blockIdx.x * RT_W, y0 = blockIdx.y * RT_H;
-    const float* __restrict__ b = band + (size_t)plane * l.plane;
+    const int x0 = blockIdx.x * R9_W, y0 = blockIdx.y * R9_H;
+    r9_load_tile(sb, band + (size_t)plane * l.plane, l, x0, y0);
     const float* __restrict__ c = coarse + (size_t)plane * lc.plane;
-    for (int i = threadIdx.x; i < RA_H * RA_W; i += 256) {
-        const int r = i / RA_W, cc = i - r * RA_W;
-        const int gy = reflect101(y0 - 4 + r, l.h), gx = reflect101(x0 - 4 + cc, l.w);
-        sb[r][cc] = __ldg(b + (size_t)gy * l.pitch + gx);
-        su[r][cc] = ((gy | gx) & 1) ? 0.f : __ldg(c + (size_t)(gy >> 1) * lc.pitch + (gx >> 1));
+    for (int i = threadIdx.x; i < RC_CH * RC_CW; i += 256) {
+        const int r = i / RC_CW, cc = i - r * RC_CW;
+        // even fine coordinates of the window (reflection keeps parity), value = coarse sample
+        const int gy = reflect101(y0 - 4 + 2 * r, l.h), gx = reflect101(x0 - 4 + 2 * cc, l.w);
+        sc[r][cc] = __ldg(c + (size_t)(gy >> 1) * lc.pitch + (gx >> 1));
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < RT_H * RT_W; i += 256) {
-        const int y = i / RT_W, x = i - y * RT_W;
-        const int gy = y0 + y, gx = x0 + x;
-        if (gy >= l.h || gx >= l.w) continue;
-        float hp = 0.f, lp = 0.f;
+    const int tx = threadIdx.x & 15, y = r9_row(threadIdx.x);
+    const int gy = y0 + y, gx = x0 + 4 * tx;
+    if (gy >= l.h || gx >= l.w) return;
+    float hp[4] = {0.f, 0.f, 0.f, 0.f}, lp[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int ky = 0; ky < 9; ++ky)
+    for (int ky = 0; ky < 9; ++ky) {
+        const float4 a0 = *reinterpret_cast<const float4*>(&sb[y + ky][4 * tx]);
+        const float4 a1 = *reinterpret_cast<const float4*>(&sb[y + ky][4 * tx + 4]);
+        const float4 a2 = *reinterpret_cast<const float4*>(&sb[y + ky][4 * tx + 8]);
+        const float v[12] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x, a2.y, a2.z, a2.w};
 #pragma unroll
-            for (int kx = 0; kx < 9; ++kx) {
-                hp = fmaf(c_hp[ky * 9 + kx], sb[y + ky][x + kx], hp);
-                lp = fmaf(2.0f * c_lp[ky * 9 + kx], su[y + ky][x + kx], lp);
-            }
-        out[(size_t)plane * l.plane + (size_t)gy * l.pitch + gx] = addr(lp, hp);
+        for (int kx = 0; kx < 9; ++kx) {
+            const float cf = c_hp[ky * 9 + kx];
+#pragma unroll
+            for (int p = 0; p < 4; ++p) hp[p] = fmaf(cf, v[p + kx], hp[p]);
+        }
     }
+    if (y & 1) rc_lowpass<1>(sc, y, tx, lp);   // warp-uniform (r9_row)
+    else rc_lowpass<0>(sc, y, tx, lp);
+    float* o = out + (size_t)plane * l.plane + (size_t)gy * l.pitch + gx;
+    *reinterpret_cast<float4*>(o) = make_float4(addr(lp[0], hp[0]), addr(lp[1], hp[1]), addr(lp[2], hp[2]), addr(lp[3], hp[3]));
 }
 
 // merge(L', a, b) -> Lab2BGR -> u8 (MagnifyCore.hpp:272-276)
@@ -334,7 +408,7 @@ mc_status RieszMode::build_pyramid(const ModeCtx& ctx) {
     // RieszPyramid::buildPyramid (RieszPyramid.cpp:215-238); the Riesz pair itself is formed in the phase kernel
     for (int i = 0; i < levels - 1; ++i) {
         const Level& l = lv[(size_t)i];
-        dim3 grid(cdiv(l.w, RT_W), cdiv(l.h, RT_H), lanes);
+        dim3 grid(cdiv(l.w, R9_W), cdiv(l.h, R9_H), lanes);
         KLAUNCH("riesz_analysis", i, k_riesz_analysis<<<grid, 256, 0, ctx.stream>>>(l, lv[(size_t)i + 1], oct[(size_t)i], cur_low[(size_t)i], oct[(size_t)i + 1]));
     }
     return MC_OK;
@@ -468,7 +542,7 @@ mc_status RieszMode::process(const ModeCtx& ctx, const FrameIO& io, const mc_par
     const float* result = oct[(size_t)levels - 1];
     for (int i = nb - 1; i >= 0; --i) {
         const Level& l = lv[(size_t)i];
-        dim3 grid(cdiv(l.w, RT_W), cdiv(l.h, RT_H), lanes);
+        dim3 grid(cdiv(l.w, R9_W), cdiv(l.h, R9_H), lanes);
         KLAUNCH("riesz_collapse", i, k_riesz_collapse<<<grid, 256, 0, ctx.stream>>>(l, lv[(size_t)i + 1], low_amp[(size_t)i], result, res[(size_t)i]));
         result = res[(size_t)i];
     }
