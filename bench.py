@@ -57,18 +57,19 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons for one GPU during the timed region."""
+    """Samples nvidia-smi clocks / throttle reasons for one GPU; started before the warm-up (nvidia-smi takes
+    ~0.2 s to emit its first row) and filtered to the rows that fall inside the timed regions."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.windows = index, [], None, []
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -77,12 +78,15 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def window(self, t0, t1):
+        self.windows.append((t0, t1))
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.1)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -90,7 +94,9 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for ts, r in self.rows:
+            if not any(t0 - 0.02 <= ts <= t1 + 0.02 for t0, t1 in self.windows):
+                continue
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
                 for n, v in zip(names, r[3:7]):
@@ -99,7 +105,8 @@ class ClockSampler:
             except Exception:
                 pass
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons),
+                "note": "nvidia-smi rows inside the device-resident and e2e timed regions"}
 
 
 def make_clip(t_frames, lanes):
@@ -219,13 +226,14 @@ def run_ours(args, rank, world, local_rank):
         return _max_over_ranks(x, dist, device="cuda")
 
     # ---- device-resident throughput ----------------------------------------------------------
-    for i in range(args.warmup):
-        step_dev(i)
-    barrier()
     vis = [v for v in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if v]
     sampler = ClockSampler(vis[local_rank] if local_rank < len(vis) else local_rank)
     if rank == 0:
         sampler.start()
+    for i in range(args.warmup):
+        step_dev(i)
+    barrier()
+    t_w0 = time.time()
     l0 = proc.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
@@ -233,10 +241,10 @@ def run_ours(args, rank, world, local_rank):
         step_dev(args.warmup + i)
     e1.record(stream)
     barrier()
+    sampler.window(t_w0, time.time())
     ms = max_over_ranks(e0.elapsed_time(e1))
     from lvm_b200.shard import sum_over_ranks
     launches = int(sum_over_ranks(float(proc.launch_count - l0), dist, device="cuda"))
-    clocks = sampler.stop() if rank == 0 else None
     fps = world * lanes * args.steps / (ms * 1e-3)
 
     # ---- end to end through the host API (pinned frames in / out, copies inside the region) ----
@@ -257,9 +265,12 @@ def run_ours(args, rank, world, local_rank):
     run_e2e(max(args.warmup, 3), 0)
     barrier()
     t0 = time.perf_counter()
+    t_w0 = time.time()
     run_e2e(args.steps, args.warmup)
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
+    sampler.window(t_w0, time.time())
+    clocks = sampler.stop() if rank == 0 else None
     e2e_fps = world * lanes * args.steps / e2e_s
     barrier()
 
@@ -342,7 +353,7 @@ def run_ours(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=400)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--lanes", type=int, default=16, help="independent 1080p streams per GPU, stepped in lock-step")

@@ -428,7 +428,7 @@ __global__ void __launch_bounds__(32 * DS_WARPS) k_down_strip(const DownArgs a) 
 // with the three Lab channels carried together; the LUT gathers (L1-bound) hide the stencil math.
 // ------------------------------------------------------------------------------------------------
 constexpr int IG_ROWS = 32;   // coarse rows per warp (halo rows re-convert 4 of 68 fine rows)
-constexpr int IG_WARPS = 4;
+constexpr int IG_WARPS = 1;   // one warp per CTA: 5k+ independent CTAs per 16-lane step, no wave-quantisation tail
 
 struct IngestArgs {
     const uint8_t* in; size_t in_step, in_lane_stride;
@@ -550,40 +550,53 @@ __global__ void __launch_bounds__(32 * IG_WARPS) k_ingest_lab(const IngestArgs a
 }
 
 // ------------------------------------------------------------------------------------------------
-// collapse (small levels): cur_l = pyrUp(cur_{l+1}) + m_l, in place in m_l.  Tile 64 x 16.
+// collapse: cur_l = pyrUp(cur_{l+1}) + m_l, in place in m_l.  Tile 64 x 32, thread block 4 x 2 (same
+// register pyrUp as the level kernel), 128-bit accesses to m_l.
 // ------------------------------------------------------------------------------------------------
-constexpr int CW = 64, CH_ = 16;
-constexpr int CDW = CW / 2 + 2, CDH = CH_ / 2 + 2;
-
 __global__ void __launch_bounds__(256) k_collapse(Level lf, Level lc, float* __restrict__ m_fine,
                                                   const float* __restrict__ m_coarse) {
-    __shared__ float sD[CDH][CDW];
-    __shared__ float sU[CDH][CW];
+    __shared__ __align__(16) float sD[DH][DP];
     const int plane = blockIdx.z;
-    const int x0 = blockIdx.x * CW, y0 = blockIdx.y * CH_;
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
     const float* __restrict__ src = m_coarse + (size_t)plane * lc.plane;
-    for (int idx = threadIdx.x; idx < CDH * CDW; idx += blockDim.x) {
-        const int k = idx / CDW, j = idx - k * CDW;
+    for (int i = threadIdx.x; i < DH * DW; i += 256) {
+        const int k = i / DW, j = i - k * DW;
         const int iy = upsrc(y0 / 2 - 1 + k, lc.h), ix = upsrc(x0 / 2 - 1 + j, lc.w);
         sD[k][j] = __ldg(src + (size_t)iy * lc.pitch + ix);
     }
     __syncthreads();
-    for (int idx = threadIdx.x; idx < CDH * CW; idx += blockDim.x) {
-        const int k = idx / CW, x = idx - k * CW;
-        const int j0 = (x >> 1) + 1;
-        sU[k][x] = (x & 1) ? (sD[k][j0] + sD[k][j0 + 1]) * 4.0f : (sD[k][j0 - 1] + sD[k][j0] * 6.0f + sD[k][j0 + 1]);
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int gx = x0 + 4 * tx;
+    if (gx >= lf.w) return;
+    float e[3][4];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        const float2 p0 = *reinterpret_cast<const float2*>(&sD[ty + q][2 * tx]);
+        const float2 p1 = *reinterpret_cast<const float2*>(&sD[ty + q][2 * tx + 2]);
+        e[q][0] = p0.x + p0.y * 6.0f + p1.x;
+        e[q][1] = (p0.y + p1.x) * 4.0f;
+        e[q][2] = p0.y + p1.x * 6.0f + p1.y;
+        e[q][3] = (p1.x + p1.y) * 4.0f;
     }
-    __syncthreads();
     float* __restrict__ mf = m_fine + (size_t)plane * lf.plane;
-    for (int idx = threadIdx.x; idx < CH_ * CW; idx += blockDim.x) {
-        const int y = idx / CW, x = idx - y * CW;
-        const int gy = y0 + y, gx = x0 + x;
-        if (gy >= lf.h || gx >= lf.w) continue;
-        const int k0 = (y >> 1) + 1;
-        const float up = (y & 1) ? ((sU[k0][x] + sU[k0 + 1][x]) * 4.0f) * kInv64
-                                 : (sU[k0 - 1][x] + sU[k0][x] * 6.0f + sU[k0 + 1][x]) * kInv64;
-        const size_t o = (size_t)gy * lf.pitch + gx;
-        mf[o] = up + mf[o];
+#pragma unroll
+    for (int ry = 0; ry < 2; ++ry) {
+        const int gy = y0 + 2 * ty + ry;
+        if (gy >= lf.h) continue;
+        float4* p = reinterpret_cast<float4*>(mf + (size_t)gy * lf.pitch + gx);   // rows padded to 32 floats
+        float4 v = *p;
+        if (ry == 0) {
+            v.x = (e[0][0] + e[1][0] * 6.0f + e[2][0]) * kInv64 + v.x;
+            v.y = (e[0][1] + e[1][1] * 6.0f + e[2][1]) * kInv64 + v.y;
+            v.z = (e[0][2] + e[1][2] * 6.0f + e[2][2]) * kInv64 + v.z;
+            v.w = (e[0][3] + e[1][3] * 6.0f + e[2][3]) * kInv64 + v.w;
+        } else {
+            v.x = ((e[1][0] + e[2][0]) * 4.0f) * kInv64 + v.x;
+            v.y = ((e[1][1] + e[2][1]) * 4.0f) * kInv64 + v.y;
+            v.z = ((e[1][2] + e[2][2]) * 4.0f) * kInv64 + v.z;
+            v.w = ((e[1][3] + e[2][3]) * 4.0f) * kInv64 + v.w;
+        }
+        *p = v;
     }
 }
 
@@ -825,7 +838,7 @@ cudaError_t launch_down(const LevelArgs& a, cudaStream_t s) {
 
 cudaError_t launch_collapse(const Level& lf, const Level& lc, float* m_fine, const float* m_coarse, int planes,
                             cudaStream_t s) {
-    dim3 grid(cdiv(lf.w, CW), cdiv(lf.h, CH_), planes);
+    dim3 grid(cdiv(lf.w, TW), cdiv(lf.h, TH), planes);
     k_collapse<<<grid, 256, 0, s>>>(lf, lc, m_fine, m_coarse);
     return cudaGetLastError();
 }
