@@ -237,58 +237,96 @@ struct AmpArgs {
     float alpha, thresh;
 };
 
-constexpr int GA_W = RT_W + 12, GA_H = RT_H + 12;
+// Tile 64 x 16, thread strip 1 x 4 (same row dealing as the 9x9 kernels is not needed here).  Row pass:
+// 16 tile values -> 4 outputs per plane with three/four 128-bit shared loads; column pass likewise from the
+// row-pass buffer; then the point-wise amplification on float4 global accesses.
+constexpr int GA_TW = 64, GA_TH = 16;
+constexpr int GA_W = GA_TW + 16, GA_H = GA_TH + 12;   // window origin (x0-8, y0-6): 8 columns of left halo keep float4 alignment
+
+__device__ __forceinline__ float g13(const Gauss13& g, const float* v) {
+    // symmetric 13-tap: centre + pairs (cv::sepFilter2D symmetric row/column filters)
+    float acc = g.k[6] * v[6];
+#pragma unroll
+    for (int j = 1; j <= 6; ++j) acc = fmaf(g.k[6 + j], v[6 - j] + v[6 + j], acc);
+    return acc;
+}
 
 __global__ void __launch_bounds__(256) k_riesz_amplify(const AmpArgs a) {
-    __shared__ float s[3][GA_H][GA_W + 1];
-    __shared__ float sr[3][GA_H][RT_W + 1];
+    __shared__ __align__(16) float s[3][GA_H][GA_W];
+    __shared__ __align__(16) float sr[3][GA_H][GA_TW];
     const int plane = blockIdx.z;
-    const int x0 = blockIdx.x * RT_W, y0 = blockIdx.y * RT_H;
+    const int x0 = blockIdx.x * GA_TW, y0 = blockIdx.y * GA_TH;
     const Level l = a.l;
     const size_t pb = (size_t)plane * l.plane;
     const float* srcs[3] = {a.amp, a.t_c, a.t_s};
-    for (int i = threadIdx.x; i < GA_H * GA_W; i += 256) {
-        const int r = i / GA_W, c = i - r * GA_W;
-        const size_t o = pb + (size_t)reflect101(y0 - 6 + r, l.h) * l.pitch + reflect101(x0 - 6 + c, l.w);
+    const bool interior = x0 >= 8 && x0 + GA_TW + 8 <= l.w && y0 >= 6 && y0 + GA_TH + 6 <= l.h;
+    if (interior) {
+        for (int i = threadIdx.x; i < GA_H * (GA_W / 4); i += 256) {
+            const int r = i / (GA_W / 4), c4 = i - r * (GA_W / 4);
+            const size_t o = pb + (size_t)(y0 - 6 + r) * l.pitch + (x0 - 8 + 4 * c4);
 #pragma unroll
-        for (int q = 0; q < 3; ++q) s[q][r][c] = __ldg(srcs[q] + o);
-    }
-    __syncthreads();
-    // row pass (symmetric kernel: centre + pairs, as cv::sepFilter2D's symmetric row filter)
-    for (int i = threadIdx.x; i < GA_H * RT_W; i += 256) {
-        const int r = i / RT_W, x = i - r * RT_W;
+            for (int q = 0; q < 3; ++q) *reinterpret_cast<float4*>(&s[q][r][4 * c4]) = __ldg(reinterpret_cast<const float4*>(srcs[q] + o));
+        }
+    } else {
+        for (int i = threadIdx.x; i < GA_H * GA_W; i += 256) {
+            const int r = i / GA_W, c = i - r * GA_W;
+            const size_t o = pb + (size_t)reflect101(y0 - 6 + r, l.h) * l.pitch + reflect101(x0 - 8 + c, l.w);
 #pragma unroll
-        for (int q = 0; q < 3; ++q) {
-            float acc = a.g.k[6] * s[q][r][x + 6];
-#pragma unroll
-            for (int j = 1; j <= 6; ++j) acc = fmaf(a.g.k[6 + j], s[q][r][x + 6 - j] + s[q][r][x + 6 + j], acc);
-            sr[q][r][x] = acc;
+            for (int q = 0; q < 3; ++q) s[q][r][c] = __ldg(srcs[q] + o);
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < RT_H * RT_W; i += 256) {
-        const int y = i / RT_W, x = i - y * RT_W;
-        const int gy = y0 + y, gx = x0 + x;
-        if (gy >= l.h || gx >= l.w) continue;
-        float b[3];
+    // row pass: item = (row r, strip of 4 columns); output column x uses window columns x+2 .. x+14
+    for (int i = threadIdx.x; i < GA_H * (GA_TW / 4); i += 256) {
+        const int r = i >> 4, tx4 = (i & 15) * 4;
 #pragma unroll
         for (int q = 0; q < 3; ++q) {
-            float acc = a.g.k[6] * sr[q][y + 6][x];
+            float v[20];
 #pragma unroll
-            for (int j = 1; j <= 6; ++j) acc = fmaf(a.g.k[6 + j], sr[q][y + 6 - j][x] + sr[q][y + 6 + j][x], acc);
-            b[q] = acc;
+            for (int j = 0; j < 5; ++j) {
+                const float4 t = *reinterpret_cast<const float4*>(&s[q][r][tx4 + 4 * j]);
+                v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+            }
+            float4 o;
+            o.x = g13(a.g, v + 2); o.y = g13(a.g, v + 3); o.z = g13(a.g, v + 4); o.w = g13(a.g, v + 5);
+            *reinterpret_cast<float4*>(&sr[q][r][tx4]) = o;
         }
-        const size_t o = pb + (size_t)gy * l.pitch + gx;
+    }
+    __syncthreads();
+    const int tx4 = (threadIdx.x & 15) * 4, y = threadIdx.x >> 4;
+    const int gy = y0 + y, gx = x0 + tx4;
+    if (gy >= l.h || gx >= l.w) return;
+    float b[3][4];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        float c0[13], c1[13], c2[13], c3[13];
+#pragma unroll
+        for (int j = 0; j < 13; ++j) {
+            const float4 t = *reinterpret_cast<const float4*>(&sr[q][y + j][tx4]);
+            c0[j] = t.x; c1[j] = t.y; c2[j] = t.z; c3[j] = t.w;
+        }
+        b[q][0] = g13(a.g, c0); b[q][1] = g13(a.g, c1); b[q][2] = g13(a.g, c2); b[q][3] = g13(a.g, c3);
+    }
+    const size_t o = pb + (size_t)gy * l.pitch + gx;
+    const float4 low4 = *reinterpret_cast<const float4*>(a.low + o);
+    const float4 rx4 = *reinterpret_cast<const float4*>(a.rx + o);
+    const float4 ry4 = *reinterpret_cast<const float4*>(a.ry + o);
+    const float lowv[4] = {low4.x, low4.y, low4.z, low4.w}, rxv[4] = {rx4.x, rx4.y, rx4.z, rx4.w}, ryv[4] = {ry4.x, ry4.y, ry4.z, ry4.w};
+    float outv[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
         // normalize() tail + amplify() (RieszPyramid.cpp:125-143)
-        const float tc = __fdiv_rn(b[1], b[0]), ts = __fdiv_rn(b[2], b[0]);
+        const float tc = __fdiv_rn(b[1][p], b[0][p]), ts = __fdiv_rn(b[2][p], b[0][p]);
         const float mag = __fsqrt_rn(addr(mulr(tc, tc), mulr(ts, ts)));
         float m2 = mulr(mag, a.alpha);
         m2 = (m2 > a.thresh) ? a.thresh : m2;                 // THRESH_TRUNC
-        const float pc = cosf(m2), ps = sinf(m2);
-        float pair = __fdiv_rn(addr(mulr(a.rx[o], tc), mulr(a.ry[o], ts)), mag);
+        float pc, ps;
+        sincosf(m2, &ps, &pc);
+        float pair = __fdiv_rn(addr(mulr(rxv[p], tc), mulr(ryv[p], ts)), mag);
         if (pair != pair) pair = 0.f;                          // patchNaNs
-        a.out[o] = subr(mulr(a.low[o], pc), mulr(pair, ps));
+        outv[p] = subr(mulr(lowv[p], pc), mulr(pair, ps));
     }
+    *reinterpret_cast<float4*>(a.out + o) = make_float4(outv[0], outv[1], outv[2], outv[3]);
 }
 
 // result_i = filter2D(injectZerosEven(nearest_up(result_{i+1})), 2*LP) + filter2D(band_i, HP)
@@ -535,7 +573,7 @@ mc_status RieszMode::process(const ModeCtx& ctx, const FrameIO& io, const mc_par
         a.out = low_amp[(size_t)i];
         gaussian_kernel_13_3(a.g.k);
         a.alpha = alpha; a.thresh = thresh;
-        dim3 grid(cdiv(a.l.w, RT_W), cdiv(a.l.h, RT_H), lanes);
+        dim3 grid(cdiv(a.l.w, GA_TW), cdiv(a.l.h, GA_TH), lanes);
         KLAUNCH("riesz_amplify", i, k_riesz_amplify<<<grid, 256, 0, ctx.stream>>>(a));
     }
     // collapse (RieszPyramid.cpp:304-325)

@@ -198,3 +198,74 @@ def test_tma_staging_equals_ldg_staging():
             assert np.array_equal(oa, ob), (w, h, t)
         for lvl in range(1, lv):
             assert np.array_equal(a.get_state("lowpassHi", lvl), b.get_state("lowpassHi", lvl))
+
+
+def test_strided_rows_through_c_abi():
+    """in_step / out_step larger than w*c (cv::Mat with padding, GL-style strides) — padding must be ignored
+    on input and left untouched on output."""
+    import ctypes as C
+    from lvm_b200 import capi
+    w, h, c, levels = 317, 203, 3, 4
+    cfg, ocfg = make_cfgs(O.MODE_LAPLACE, 20, 50.0, 0.4, 3.0, 0, levels)
+    proc, oproc = L.MagnificationProcessor(0), O.MagnificationProcessor()
+    in_step, out_step = w * c + 13, w * c + 29
+    lib = capi.lib()
+    p = L.processor._to_mc(cfg)
+    for t in range(4):
+        f = synth_frame(t, w, h, c)
+        src = np.full((h, in_step), 0xAB, np.uint8)
+        src[:, :w * c] = f.reshape(h, w * c)
+        dst = np.full((h, out_step), 0xCD, np.uint8)
+        produced = C.c_int(0)
+        st = lib.mc_process(proc._h, src.ctypes.data, w, h, c, in_step, C.byref(p), dst.ctypes.data, out_step, C.byref(produced))
+        assert st == 0 and produced.value == 1
+        _, ref = oproc.process(f, ocfg)
+        assert int(u8_diff(dst[:, :w * c].reshape(h, w, c), ref).max()) <= 1
+        assert (dst[:, w * c:] == 0xCD).all()
+
+
+def test_levels_clamp_and_zero_amplification_properties():
+    """levels above calculateMaxLevels are clamped (MagnificationProcessor.cpp:34); alpha = 0 makes every gain
+    min(0, .) <= 0 ... = 0 only when the wavelength term is positive, so instead use the exact property that a
+    static clip has a zero band-pass: output == the first-frame (Lab round-trip) output for every frame."""
+    w, h, c = 322, 241, 3
+    cfg, ocfg = make_cfgs(O.MODE_LAPLACE, 20, 50.0, 0.4, 3.0, 50, 20)     # levels = 20 -> clamped to 6
+    assert L.calculateMaxLevels(w, h) == 6
+    proc, oproc = L.MagnificationProcessor(0), O.MagnificationProcessor()
+    f = synth_frame(3, w, h, c)
+    first = None
+    for t in range(5):
+        produced, out = proc.process_image(f, cfg)
+        _, oout = oproc.process(f, ocfg)
+        assert produced and int(u8_diff(out, oout).max()) <= 1
+        if first is None:
+            first = out
+        else:
+            assert np.array_equal(out, first), t      # identical frames -> hi == lo == band -> motion == 0 exactly
+    assert proc.get_state("lowpassHi", 5) is not None and proc.get_state("lowpassHi", 6) is None
+
+
+def test_config5_4k_8_levels():
+    w, h, levels = 3840, 2160, 8
+    cfg, ocfg = make_cfgs(O.MODE_LAPLACE, 20, 50.0, 0.4, 3.0, 0, levels)
+    proc, oproc = L.MagnificationProcessor(0), O.MagnificationProcessor()
+    proc.set_option("keep_float_output", 1)
+    for t in range(3):
+        f = synth_frame(t, w, h, 3)
+        dbg = {}
+        _, out = proc.process_image(f, cfg)
+        _, oout = oproc.process(f, ocfg, dbg)
+        assert float(np.abs(proc.float_output(w, h, 3)[0] - dbg["output_bgr_f32"]).max()) < F32_TOL
+        assert int(u8_diff(out, oout).max()) <= 1
+
+
+def test_empty_image_and_mode_none_free_state():
+    proc = L.MagnificationProcessor(0)
+    cfg, _ = make_cfgs(O.MODE_LAPLACE, 20, 50.0, 0.4, 3.0, 0, 4)
+    proc.process_image(synth_frame(0, 64, 48, 3), cfg)
+    assert proc.get_state("lowpassHi", 1) is not None
+    produced, out = proc.process_image(np.zeros((0, 0, 3), np.uint8), cfg)        # empty image: identity, state dropped
+    assert not produced
+    assert proc.state_dims("lowpassHi", 1)[0] == 0
+    produced, _ = proc.process_image(synth_frame(1, 64, 48, 3), cfg)              # starts again as a first frame
+    assert produced
