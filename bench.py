@@ -146,7 +146,7 @@ def time_oracle(n_warm, n_frames):
 
 def run_reference(args, rank, world):
     if rank != 0:
-        return
+        return None
     per_step = args.ref_frames_per_step
     import cv2
     from lvm_b200.synth import synth_frame
@@ -164,7 +164,7 @@ def run_reference(args, rank, world):
     dt = time.perf_counter() - t0
     fps = args.steps * per_step / dt
     sample = f"{args.steps} steps x {per_step} frames of the 1080p workload, cv2 {cv2.__version__}, {cores} threads"
-    print(json.dumps({
+    return json.dumps({
         "impl": "reference", "metric": "1080p frames/sec (Laplace, 6-level)", "value": fps, "unit": "frames/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -172,7 +172,7 @@ def run_reference(args, rank, world):
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    })
 
 
 def run_ours(args, rank, world, local_rank):
@@ -187,7 +187,6 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         import torch.distributed as dist_
         dist = dist_
-        os.environ.setdefault("NCCL_DEBUG", "WARN")   # keep stdout to the single JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     # one-time broadcast of the parameter block from rank 0 (the path's only collective)
@@ -333,8 +332,9 @@ def run_ours(args, rank, world, local_rank):
         cpu = {"value": v, "unit": "frames/s", "cores": cores, "kind": "port",
                "sample": f"{args.cpu_frames} frames of the same 1080p clip through the cv2 oracle ({dt:.1f} s)"}
 
+    line = None
     if rank == 0:
-        print(json.dumps({
+        line = json.dumps({
             "metric": "1080p frames/sec (Laplace, 6-level)", "value": fps, "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -344,10 +344,28 @@ def run_ours(args, rank, world, local_rank):
             "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": frame_bytes,
                     "d2h_bytes_per_step": frame_bytes, "pipeline_depth": depth},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
-        }))
+        })
     if dist:
         dist.barrier()
         dist.destroy_process_group()
+    return line
+
+
+class StdoutToStderr:
+    """Everything but the final JSON line goes to stderr — NCCL (NCCL_DEBUG=VERSION/INFO), torch and cuFFT log
+    to fd 1, and the contract is ONE JSON line on stdout."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
 
 
 def main():
@@ -365,12 +383,15 @@ def main():
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
-    if args.impl == "reference":
-        run_reference(args, rank, world)
-    else:
-        if args.warmup < 3:
-            args.warmup = 3
-        run_ours(args, rank, world, local_rank)
+    with StdoutToStderr():
+        if args.impl == "reference":
+            line = run_reference(args, rank, world)
+        else:
+            if args.warmup < 3:
+                args.warmup = 3
+            line = run_ours(args, rank, world, local_rank)
+    if line is not None:
+        print(line, flush=True)
 
 
 if __name__ == "__main__":
