@@ -417,7 +417,8 @@ mc_status mc_submit(mc_handle* h, const uint8_t* in, int width, int height, int 
     }
     const size_t rows = (size_t)height * h->lanes;
     if (is_pinned(in)) {
-        CK(cudaMemcpy2DAsync(s.d_in, row, in, in_step, row, rows, cudaMemcpyHostToDevice, h->s_in));
+        if (in_step == row) CK(cudaMemcpyAsync(s.d_in, in, bytes, cudaMemcpyHostToDevice, h->s_in));
+        else CK(cudaMemcpy2DAsync(s.d_in, row, in, in_step, row, rows, cudaMemcpyHostToDevice, h->s_in));
     } else {
         for (size_t r = 0; r < rows; ++r) std::memcpy(s.h_in + r * row, in + r * in_step, row);
         CK(cudaMemcpyAsync(s.d_in, s.h_in, bytes, cudaMemcpyHostToDevice, h->s_in));
@@ -432,7 +433,8 @@ mc_status mc_submit(mc_handle* h, const uint8_t* in, int width, int height, int 
     if (produced) {
         CK(cudaStreamWaitEvent(h->s_out, s.ev_k, 0));
         if (out && is_pinned(out)) {
-            CK(cudaMemcpy2DAsync(out, out_step, s.d_out, row, row, rows, cudaMemcpyDeviceToHost, h->s_out));
+            if (out_step == row) CK(cudaMemcpyAsync(out, s.d_out, bytes, cudaMemcpyDeviceToHost, h->s_out));
+            else CK(cudaMemcpy2DAsync(out, out_step, s.d_out, row, row, rows, cudaMemcpyDeviceToHost, h->s_out));
             s.direct_out = true;
         } else if (out) {
             CK(cudaMemcpyAsync(s.h_out, s.d_out, bytes, cudaMemcpyDeviceToHost, h->s_out));
