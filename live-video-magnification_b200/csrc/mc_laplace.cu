@@ -713,7 +713,7 @@ __global__ void __launch_bounds__(256) k_egress(const EgressArgs a) {
                     B = B + up[C > 2 ? 2 : 0][ry][i] * a.chroma;
                 }
                 float ob, og, orr;
-                lab_to_bgr(L, A, B, a.coeffs, a.gtab, ob, og, orr);
+                lab_to_bgr_fast(L, A, B, a.coeffs, a.gtab, ob, og, orr);
                 of[3 * i] = ob; of[3 * i + 1] = og; of[3 * i + 2] = orr;
                 // lab_to_bgr clips to [0,1] before the gamma spline, so the saturating branches of
                 // convertTo reduce to a min with 255 (NaN -> 0 by the conversion itself)

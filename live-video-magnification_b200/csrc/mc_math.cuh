@@ -185,6 +185,41 @@ MC_HD void lab_to_bgr(float L, float a, float b, const LabInvCoeffs& k, const fl
     orr = inv_gamma(vr, gtab);
 }
 
+#if defined(__CUDACC__)
+// Device-only, branch-lean form of lab_to_bgr for the egress kernels: identical arithmetic for the XYZ part
+// (selects instead of branches), the [0,1] clip folded into saturating adds, and the gamma evaluated as
+// 1.055 * 2^(log2(v)/2.4) - 0.055 with lg2/ex2.approx.ftz; only when one of the three linear values is below
+// 8/1024 (where OpenCV's spline departs from the analytic curve) is the spline table consulted.
+__device__ __forceinline__ float mc_lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float mc_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+__device__ __forceinline__ void lab_to_bgr_fast(float L, float a, float b, const LabInvCoeffs& k,
+                                                const float4* __restrict__ gtab, float& ob, float& og, float& orr) {
+    const float y_lin = L * (1.0f / 903.3f);
+    const float fy_lin = 7.787f * y_lin + 16.0f / 116.0f;
+    const float fy_cub = (L + 16.0f) * (1.0f / 116.0f);
+    const bool lo = L <= 8.0f;
+    const float fy = lo ? fy_lin : fy_cub;
+    const float Y = lo ? y_lin : fy_cub * fy_cub * fy_cub;
+    const float fx = a * (1.0f / 500.0f) + fy;
+    const float fz = fy - b * (1.0f / 200.0f);
+    const float fth = 6.0f / 29.0f;
+    const float X = fx <= fth ? (fx - 16.0f / 116.0f) * (1.0f / 7.787f) : fx * fx * fx;
+    const float Z = fz <= fth ? (fz - 16.0f / 116.0f) * (1.0f / 7.787f) : fz * fz * fz;
+    const float vb = __saturatef(k.c[0] * X + k.c[1] * Y + k.c[2] * Z);
+    const float vg = __saturatef(k.c[3] * X + k.c[4] * Y + k.c[5] * Z);
+    const float vr = __saturatef(k.c[6] * X + k.c[7] * Y + k.c[8] * Z);
+    ob = fmaf(1.055f, mc_ex2(mc_lg2(vb) * (1.0f / 2.4f)), -0.055f);
+    og = fmaf(1.055f, mc_ex2(mc_lg2(vg) * (1.0f / 2.4f)), -0.055f);
+    orr = fmaf(1.055f, mc_ex2(mc_lg2(vr) * (1.0f / 2.4f)), -0.055f);
+    if (fminf(vb, fminf(vg, vr)) < 8.0f / 1024.0f) {   // dark end: OpenCV's spline, per channel
+        if (vb < 8.0f / 1024.0f) ob = spline_gamma(vb, gtab);
+        if (vg < 8.0f / 1024.0f) og = spline_gamma(vg, gtab);
+        if (vr < 8.0f / 1024.0f) orr = spline_gamma(vr, gtab);
+    }
+}
+#endif
+
 // iirFilter (TemporalFilter.cpp:9-22): cv::addWeighted rounds once from a double sum.
 MC_HD float ema(float state, float x, double one_minus_c, double c) {
     return (float)((double)state * one_minus_c + (double)x * c);
