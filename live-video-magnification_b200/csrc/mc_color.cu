@@ -313,9 +313,13 @@ mc_status ColorMode::process(const ModeCtx& ctx, const FrameIO& io, const mc_par
     if (count < 2) return MC_OK;  // MagnifyCore.hpp:180 (passthrough)
     const int n = count;
     if (head != 0 && n != ring_cap) {
-        // window is not cyclically contiguous (capacity grew beyond a shrunk window): compact it
-        *ctx.err = "color window: unsupported capacity change";
-        return MC_ERR_UNSUPPORTED;
+        // The frame rate was lowered while the ring was only partly filled: the window no longer occupies a
+        // cyclically contiguous slot range.  Compact it into logical order (rare, so plain column copies).
+        for (int t = 0; t < n; ++t)
+            MCK(cudaMemcpyAsync(work + (size_t)t * S, ring + (size_t)((head + t) % ring_cap) * S, S * sizeof(float),
+                                cudaMemcpyDeviceToDevice, ctx.stream));
+        std::swap(ring, work);
+        head = 0;
     }
 
     // ideal temporal band-pass (TemporalFilter.cpp:24-57) on the physical column order

@@ -65,3 +65,19 @@ def test_color_lanes_match_single():
         if pm:
             for k in range(2):
                 assert int(u8_diff(mo[k], outs[k][1]).max()) <= 1
+
+
+def test_color_framerate_changes_keep_window_semantics():
+    """framerate is a live parameter: the window cap getOptimalBufferSize(int(fps)) grows (16 -> 64) and shrinks
+    (64 -> 16, also while the ring is only partly filled) without a reset; the DFT length follows the window."""
+    w, h, c, levels = 160, 120, 3, 2
+    proc, oproc = L.MagnificationProcessor(0), O.MagnificationProcessor()
+    fps_seq = [8.0] * 20 + [30.0] * 30 + [8.0] * 12 + [30.0] * 6 + [7.0] * 10
+    for t, fps in enumerate(fps_seq):
+        cfg, ocfg = make_cfgs(O.MODE_COLOR, 100, 0.0, 0.8, 1.2, 0, levels, fps)
+        f = synth_frame(t, w, h, c, fps=8.0)
+        produced, out = proc.process_image(f, cfg)
+        oprod, oout = oproc.process(f, ocfg)
+        assert produced == oprod, t
+        if produced:
+            assert int(u8_diff(out, oout).max()) <= 1, (t, fps, oproc.color.window.shape)
