@@ -141,9 +141,13 @@ void* mc_stream(mc_handle* h);
 mc_status mc_set_option(mc_handle* h, const char* key, int value);
 
 /* Test-only access to temporal state planes as dense f32 [lanes][channels][rows][cols].
- * Names: Laplace "lowpassHi"/"lowpassLo" (MotionState, MagnifyCore.hpp:24-29), level 0..levels;
- * Color "window" (level ignored; [lanes][C][cols=frames][rows=pixels], logical order oldest first);
- * Phase "old.lowpass","old.rx","old.ry","lo.phase.c","lo.phase.s","lo.r0.c",... (RieszState).
+ * Names: Laplace "lowpassHi" / "lowpassLo" (MotionState, MagnifyCore.hpp:24-29), level 0..levels (levels 0 and
+ *   `levels` exist only with option faithful_level0);
+ * Phase, per band level 0..levels-2, one channel: "old.lowpass", "old.rx", "old.ry" (RieszState::old),
+ *   "phase.c", "phase.s" (itsPhase — the two filters' copies are identical), "lo.r0.c", "lo.r0.s", "lo.r1.c",
+ *   "lo.r1.s", "hi.r0.c", "hi.r0.s", "hi.r1.c", "hi.r1.s" (itsRegister0/1 of the low / high cutoff filters,
+ *   TemporalFilter.cpp:299-317);
+ * Color keeps its rolling window in a device ring buffer that is not exposed.
  * mc_state_dims reports rows/cols/channels for a name+level (0 rows if absent). */
 mc_status mc_state_dims(mc_handle* h, const char* name, int level, int* rows, int* cols, int* channels);
 mc_status mc_get_state(mc_handle* h, const char* name, int level, float* dst, size_t dst_floats);

@@ -211,9 +211,9 @@ void ColorMode::reset() {
     plan_n = 0;
     arena.release();
     lv.clear(); G.clear(); U.clear(); ulv.clear();
-    ring = work = nullptr; spec = nullptr; minmax = nullptr; filtered_small = nullptr;
+    ring = work = nullptr; spec = nullptr; minmax = nullptr;
     allocated = false;
-    count = head = cap = 0;
+    count = head = 0;
     ring_cap = 0;
     mask_dev = nullptr;
     mask_cap = 0;
@@ -264,21 +264,20 @@ mc_status ColorMode::process(const ModeCtx& ctx, const FrameIO& io, const mc_par
     const size_t S = (size_t)planes * small_rows;  // signals (pixels x channels x lanes)
     // ring capacity: grows when the framerate asks for a longer window (rare); contents are kept in
     // logical order so the invariant "head == 0 or count == capacity" holds.
-    if (cap < want_cap || ring == nullptr) {
-        const int new_cap = std::max(want_cap, std::max(cap, 2));
+    if (ring_cap < want_cap || ring == nullptr) {
+        const int new_cap = std::max(want_cap, std::max(ring_cap, 2));
         float *nring = nullptr, *nwork = nullptr;
         void* nspec = nullptr;
         MCK(arena.alloc(&nring, (size_t)new_cap * S));
         MCK(arena.alloc(&nwork, (size_t)new_cap * S));
         MCK(arena.alloc_bytes(&nspec, sizeof(cufftComplex) * (size_t)(new_cap / 2 + 1) * S));
         for (int t = 0; t < count; ++t)
-            MCK(cudaMemcpyAsync(nring + (size_t)t * S, ring + (size_t)((head + t) % cap) * S, S * sizeof(float),
+            MCK(cudaMemcpyAsync(nring + (size_t)t * S, ring + (size_t)((head + t) % ring_cap) * S, S * sizeof(float),
                                 cudaMemcpyDeviceToDevice, ctx.stream));
         ring = nring; work = nwork; spec = (cufftComplex*)nspec;
         head = 0;
         ring_cap = new_cap;
     }
-    cap = std::max(cap, want_cap);
 
     // ingest + Gaussian chain (SpatialFilter.cpp:13-23)
     {

@@ -100,7 +100,6 @@ struct ColorMode {
     int lanes = 1;
     bool allocated = false;
     int levels = 0, channels = 0, w = 0, h = 0;
-    int cap = 0;            // ring capacity = getOptimalBufferSize(int(framerate))
     int count = 0;          // frames currently in the window
     int head = 0;           // physical slot of the OLDEST column
     std::vector<Level> lv;  // gaussian chain levels 0..levels
@@ -111,9 +110,8 @@ struct ColorMode {
     float* work = nullptr;      // gathered/filtered window [planes*rows][n]
     cufftComplex* spec = nullptr;
     float* minmax = nullptr;    // device scalars
-    float* filtered_small = nullptr;
     int small_rows = 0;         // pixels of the small level
-    int ring_cap = 0;           // physical slots allocated
+    int ring_cap = 0;           // physical slots allocated (>= getOptimalBufferSize(int(framerate)))
     void* mask_dev = nullptr;
     int mask_cap = 0;
     cufftHandle plan_r2c = 0, plan_c2r = 0;
