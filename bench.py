@@ -389,7 +389,7 @@ def main():
     ap.add_argument("--lanes", type=int, default=16, help="independent 1080p streams per GPU, stepped in lock-step")
     ap.add_argument("--clip-frames", type=int, default=8)
     ap.add_argument("--cpu-frames", type=int, default=48)
-    ap.add_argument("--ref-frames-per-step", type=int, default=2)
+    ap.add_argument("--ref-frames-per-step", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
