@@ -383,10 +383,10 @@ class StdoutToStderr:
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--lanes", type=int, default=16, help="independent 1080p streams per GPU, stepped in lock-step")
+    ap.add_argument("--lanes", type=int, default=32, help="independent 1080p streams per GPU, stepped in lock-step")
     ap.add_argument("--clip-frames", type=int, default=8)
     ap.add_argument("--cpu-frames", type=int, default=48)
     ap.add_argument("--ref-frames-per-step", type=int, default=1)
