@@ -13,7 +13,7 @@ int main() {
         cfg.magnification.coLow = 0.08; cfg.magnification.coHigh = 0.46; cfg.magnification.levels = 4;
         auto f = std::make_shared<Frame>();
         f->image = cv::Mat(48, 64, CV_8UC3);
-        std::memset(f->image.data, 90, f->image.store.size());
+        std::memset(f->image.data, 90, f->image.step * (size_t)f->image.rows);
         f->seq = 42;
         FrameRef out = proc.process(f, cfg);
         if (out == f || out->seq != 42 || out->image.data == f->image.data) { std::puts("FAIL"); return 1; }
