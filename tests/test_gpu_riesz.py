@@ -127,3 +127,18 @@ def test_config3_1080p():
         if produced:
             d8 = u8_diff(out, oout)
             assert int(d8.max()) <= 3 and float((d8 == 0).mean()) >= 0.995, (t, int(d8.max()), float((d8 == 0).mean()))
+
+
+def test_riesz_lanes_match_single():
+    """A 2-lane handle (two independent streams stepped in lock-step) equals two 1-lane handles bit for bit."""
+    cfg, _ = make_cfgs(O.MODE_PHASE, 50, 50.0, 0.4, 3.0, 0, 3)
+    singles = [L.MagnificationProcessor(0) for _ in range(2)]
+    multi = L.MagnificationProcessor(0, lanes=2)
+    for t in range(6):
+        frames = [synth_frame(t, 160, 120, 3, seed=70 * k) for k in range(2)]
+        outs = [p.process_image(f, cfg) for p, f in zip(singles, frames)]
+        pm, mo = multi.process_image(np.stack(frames), cfg)
+        assert pm == outs[0][0] == outs[1][0]
+        if pm:
+            for k in range(2):
+                assert np.array_equal(mo[k], outs[k][1]), (t, k)
