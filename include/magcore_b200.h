@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define MC_ABI_VERSION 1
+#define MC_ABI_VERSION 2
 
 typedef struct mc_handle mc_handle;
 
@@ -109,6 +109,25 @@ mc_status mc_process_device(mc_handle* h, const uint8_t* d_in, int width, int he
                             size_t in_step, const mc_params* p, uint8_t* d_out, size_t out_step,
                             int* produced);
 mc_status mc_sync(mc_handle* h);
+
+/* --- "next" row: the whole processing chain of one frame on the device ---------------------
+ * Replaces runChainOnce(chain, in, cfg, original) (reference src/processing/ChainBuilder.cpp:19-29) over
+ * PreprocessProcessor (ROI crop + INTER_AREA downscale, PreprocessProcessor.cpp:10-51), GrayscaleProcessor
+ * (BGR2GRAY, GrayscaleProcessor.cpp:7-16) and MagnificationProcessor: the raw frame is uploaded once, both
+ * front stages run bit-exact on the B200, the magnification core runs on their result, and the processed frame
+ * plus the "original" tap (the pre-magnification frame, ChainBuilder.cpp:25) come back.  lanes must be 1.
+ * `out` / `original` are written tight (step = width * channels); the *_is_input flags mirror the reference
+ * returning the very same FrameRef (nothing written). */
+typedef struct mc_chain_info {
+    int32_t cur_is_input;                    /* processed frame == the input FrameRef */
+    int32_t out_w, out_h, out_channels;      /* geometry of `out` when cur_is_input == 0 */
+    int32_t orig_is_input;                   /* original tap == the input FrameRef */
+    int32_t orig_w, orig_h, orig_channels;   /* geometry of `original` when orig_is_input == 0 */
+    int32_t magnified;                       /* the magnification stage produced a frame */
+} mc_chain_info;
+mc_status mc_chain_process(mc_handle* h, const uint8_t* in, int width, int height, int channels, size_t in_step,
+                           const mc_params* p, int grayscale, uint8_t* out, size_t out_bytes, uint8_t* original,
+                           size_t original_bytes, mc_chain_info* info);
 
 /* Pipelined host path: mc_submit enqueues H2D + kernels + D2H for one frame asynchronously on
  * three streams (copy-in, compute, copy-out) and returns; mc_collect waits for the OLDEST

@@ -23,6 +23,12 @@ class McParams(C.Structure):
     ]
 
 
+class McChainInfo(C.Structure):
+    _fields_ = [("cur_is_input", C.c_int32), ("out_w", C.c_int32), ("out_h", C.c_int32), ("out_channels", C.c_int32),
+                ("orig_is_input", C.c_int32), ("orig_w", C.c_int32), ("orig_h", C.c_int32), ("orig_channels", C.c_int32),
+                ("magnified", C.c_int32)]
+
+
 # name -> (restype, argtypes); every symbol include/magcore_b200.h declares
 _u8p, _f32p, _vp = C.POINTER(C.c_uint8), C.POINTER(C.c_float), C.c_void_p
 _PP = C.POINTER(McParams)
@@ -42,6 +48,8 @@ SIGNATURES = {
     "mc_process": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_size_t, _PP, _vp, C.c_size_t, C.POINTER(C.c_int)]),
     "mc_process_device": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_size_t, _PP, _vp, C.c_size_t, C.POINTER(C.c_int)]),
     "mc_sync": (C.c_int, [_vp]),
+    "mc_chain_process": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_size_t, _PP, C.c_int, _vp, C.c_size_t, _vp,
+                                   C.c_size_t, C.POINTER(McChainInfo)]),
     "mc_pipeline_depth": (C.c_int, [_vp]),
     "mc_submit": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_size_t, _PP, _vp, C.c_size_t]),
     "mc_collect": (C.c_int, [_vp, C.POINTER(C.c_int)]),

@@ -56,6 +56,12 @@ struct mc_handle {
     float* float_out = nullptr;
     size_t float_out_floats = 0;
 
+    // mc_chain_process scratch (raw frame, preprocessed frame, gray frame, magnified frame, INTER_AREA taps)
+    uint8_t *c_raw = nullptr, *c_pre = nullptr, *c_gray = nullptr, *c_out = nullptr;
+    size_t c_raw_b = 0, c_pre_b = 0, c_gray_b = 0, c_out_b = 0;
+    void* c_tabs = nullptr;
+    size_t c_tabs_b = 0;
+
     // pipeline
     std::vector<Slot> slots;
     std::deque<int> inflight;
@@ -335,6 +341,11 @@ void mc_destroy(mc_handle* h) {
     reset_modes(h);
     free_slots(h);
     if (h->float_out) cudaFree(h->float_out);
+    if (h->c_raw) cudaFree(h->c_raw);
+    if (h->c_pre) cudaFree(h->c_pre);
+    if (h->c_gray) cudaFree(h->c_gray);
+    if (h->c_out) cudaFree(h->c_out);
+    if (h->c_tabs) cudaFree(h->c_tabs);
     if (h->tables.lab_lut) cudaFree(h->tables.lab_lut);
     if (h->tables.inv_gamma) cudaFree(h->tables.inv_gamma);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -562,5 +573,111 @@ extern "C" mc_status mc_profile_read(mc_handle* h, char* buf, size_t cap) {
     }
     if (out.size() + 1 > cap) { h->err = "profile buffer too small"; return MC_ERR_INVALID; }
     std::memcpy(buf, out.c_str(), out.size() + 1);
+    return MC_OK;
+}
+
+namespace {
+mc_status grow(mc_handle* h, uint8_t** p, size_t* cap, size_t need) {
+    if (need <= *cap) return MC_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr; *cap = 0;
+    CK(cudaMalloc((void**)p, need));
+    *cap = need;
+    return MC_OK;
+}
+}  // namespace
+
+// runChainOnce (ChainBuilder.cpp:19-29) = Preprocess -> Grayscale -> Magnification, fused on the device.
+extern "C" mc_status mc_chain_process(mc_handle* h, const uint8_t* in, int width, int height, int channels, size_t in_step,
+                                      const mc_params* p, int grayscale, uint8_t* out, size_t out_bytes, uint8_t* original,
+                                      size_t original_bytes, mc_chain_info* info) {
+    if (!h || !p || !info) return MC_ERR_INVALID;
+    std::memset(info, 0, sizeof(*info));
+    info->cur_is_input = 1; info->orig_is_input = 1;
+    CK(cudaSetDevice(h->device));
+    if (h->lanes != 1) { h->err = "mc_chain_process needs a 1-lane handle"; return MC_ERR_INVALID; }
+    if (!h->inflight.empty()) { h->err = "mc_chain_process called with pipelined frames in flight"; return MC_ERR_INVALID; }
+    int produced = 0;
+    if (in == nullptr || width <= 0 || height <= 0) {   // empty image: every stage is an identity (PreprocessProcessor.cpp:11)
+        return process_device_impl(h, nullptr, 0, 0, channels, 0, p, nullptr, 0, &produced);
+    }
+    if (channels != 1 && channels != 3) { h->err = "channels must be 1 or 3"; return MC_ERR_INVALID; }
+    const size_t row = (size_t)width * channels;
+    if (in_step < row) { h->err = "step too small"; return MC_ERR_INVALID; }
+    mc_status st;
+    if ((st = grow(h, &h->c_raw, &h->c_raw_b, row * height)) != MC_OK) return st;
+    CK(cudaMemcpy2DAsync(h->c_raw, row, in, in_step, row, (size_t)height, cudaMemcpyHostToDevice, h->stream));
+
+    // ---- PreprocessProcessor::process (PreprocessProcessor.cpp:10-51)
+    const int divisor = std::min(std::max((int)p->pre_downscale, 1), 8);
+    const bool pre_active = p->pre_roiEnabled != 0 || divisor != 1;
+    const uint8_t* cur = h->c_raw;
+    int cw = width, chh = height, cc = channels;
+    if (pre_active) {
+        int rx, ry, rw, rh;
+        preprocess_roi(width, height, p->pre_roiEnabled != 0, p->pre_roiX, p->pre_roiY, p->pre_roiW, p->pre_roiH, rx, ry, rw, rh);
+        const int dw = divisor > 1 ? std::max(1, rw / divisor) : rw, dh = divisor > 1 ? std::max(1, rh / divisor) : rh;
+        if ((st = grow(h, &h->c_pre, &h->c_pre_b, (size_t)dw * dh * channels)) != MC_OK) return st;
+        const AreaTap *dxt = nullptr, *dyt = nullptr;
+        const int *dxo = nullptr, *dyo = nullptr;
+        if (divisor > 1) {
+            std::vector<AreaTap> xt, yt;
+            std::vector<int> xo, yo;
+            build_area_tab(rw, dw, (double)rw / dw, xt, xo);
+            build_area_tab(rh, dh, (double)rh / dh, yt, yo);
+            const size_t bx = xt.size() * sizeof(AreaTap), by = yt.size() * sizeof(AreaTap), box = xo.size() * sizeof(int), boy = yo.size() * sizeof(int);
+            uint8_t* tb = (uint8_t*)h->c_tabs;
+            size_t tcap = h->c_tabs_b;
+            if ((st = grow(h, &tb, &tcap, bx + by + box + boy + 64)) != MC_OK) return st;
+            h->c_tabs = tb; h->c_tabs_b = tcap;
+            // the tables are small (a few KB); synchronous copies keep their host vectors alive long enough
+            CK(cudaStreamSynchronize(h->stream));
+            CK(cudaMemcpy(tb, xt.data(), bx, cudaMemcpyHostToDevice));
+            CK(cudaMemcpy(tb + bx, yt.data(), by, cudaMemcpyHostToDevice));
+            CK(cudaMemcpy(tb + bx + by, xo.data(), box, cudaMemcpyHostToDevice));
+            CK(cudaMemcpy(tb + bx + by + box, yo.data(), boy, cudaMemcpyHostToDevice));
+            dxt = (const AreaTap*)tb; dyt = (const AreaTap*)(tb + bx);
+            dxo = (const int*)(tb + bx + by); dyo = (const int*)(tb + bx + by + box);
+        }
+        uint8_t* gray = nullptr;
+        if (grayscale && channels == 3) {
+            if ((st = grow(h, &h->c_gray, &h->c_gray_b, (size_t)dw * dh)) != MC_OK) return st;
+            gray = h->c_gray;
+        }
+        CK(launch_preprocess(h->c_raw + (size_t)ry * row + (size_t)rx * channels, row, channels, rw, rh, dw, dh, divisor == 1,
+                             dxt, dxo, dyt, dyo, h->c_pre, gray, h->stream));
+        ++h->launches;
+        cur = h->c_pre; cw = dw; chh = dh;
+        info->orig_is_input = 0; info->orig_w = dw; info->orig_h = dh; info->orig_channels = channels;
+        if (original) {
+            if (original_bytes < (size_t)dw * dh * channels) { h->err = "original buffer too small"; return MC_ERR_INVALID; }
+            CK(cudaMemcpyAsync(original, h->c_pre, (size_t)dw * dh * channels, cudaMemcpyDeviceToHost, h->stream));
+        }
+        if (gray) { cur = gray; cc = 1; }
+    } else if (grayscale && channels == 3) {
+        // ---- GrayscaleProcessor::process alone (GrayscaleProcessor.cpp:7-16)
+        if ((st = grow(h, &h->c_gray, &h->c_gray_b, (size_t)width * height)) != MC_OK) return st;
+        CK(launch_preprocess(h->c_raw, row, 3, width, height, width, height, true, nullptr, nullptr, nullptr, nullptr, nullptr,
+                             h->c_gray, h->stream));
+        ++h->launches;
+        cur = h->c_gray; cc = 1;
+    }
+    const bool cur_is_raw = cur == h->c_raw;
+
+    // ---- MagnificationProcessor::process on the chain's current frame
+    const size_t crow = (size_t)cw * cc;
+    if ((st = grow(h, &h->c_out, &h->c_out_b, crow * chh)) != MC_OK) return st;
+    st = process_device_impl(h, cur, cw, chh, cc, crow, p, h->c_out, crow, &produced);
+    if (st != MC_OK) return st;
+    info->magnified = produced;
+    const uint8_t* result = produced ? h->c_out : cur;
+    if (produced || !cur_is_raw) {
+        info->cur_is_input = 0; info->out_w = cw; info->out_h = chh; info->out_channels = cc;
+        if (out) {
+            if (out_bytes < crow * chh) { h->err = "out buffer too small"; return MC_ERR_INVALID; }
+            CK(cudaMemcpyAsync(out, result, crow * chh, cudaMemcpyDeviceToHost, h->stream));
+        }
+    }
+    CK(cudaStreamSynchronize(h->stream));
     return MC_OK;
 }

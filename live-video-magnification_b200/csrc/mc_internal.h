@@ -2,6 +2,7 @@
 // launchers (mc_laplace.cu, mc_color.cu, mc_riesz.cu).  Not part of the C ABI.
 #pragma once
 #include <cuda_runtime.h>
+#include <cmath>
 #include <cstddef>
 #include <cstdint>
 #include <string>
@@ -41,6 +42,8 @@ int optimal_buffer_size(int fps);
 void butterworth(unsigned order, double wn, std::vector<double>& a, std::vector<double>& b);
 void motion_gains(double amplification, double coWavelength, int levels, int w, int h, std::vector<float>& gains);
 void gaussian_kernel_13_3(float taps[13]);
+void build_area_tab(int ssize, int dsize, double scale, std::vector<AreaTap>& tab, std::vector<int>& ofs);
+void preprocess_roi(int cols, int rows, bool enabled, float rx, float ry, float rw, float rh, int& x, int& y, int& w, int& h);
 
 // ------------------------------------------------------------------------------------------------
 // Laplace launchers (mc_laplace.cu).  All take the handle's stream; every call is one kernel launch
@@ -98,6 +101,11 @@ cudaError_t launch_collapse(const Level& lf, const Level& lc, float* m_fine, con
 cudaError_t launch_egress(const FrameIO& io, const DeviceTables& tb, const int16_t* lab, int pitch16, size_t plane16,
                           const float* m1, const Level& l1, const float* c2, const Level& l2, float chroma,
                           float* float_out_or_null, cudaStream_t s);
+
+// PreprocessProcessor + GrayscaleProcessor on the device (mc_preprocess.cu)
+cudaError_t launch_preprocess(const uint8_t* src_roi, size_t step, int cn, int sw, int sh, int dw, int dh, bool copy_only,
+                              const AreaTap* xtab, const int* xofs, const AreaTap* ytab, const int* yofs, uint8_t* dst,
+                              uint8_t* gray, cudaStream_t s);
 
 // plane copy helpers
 cudaError_t launch_copy_planes(float* dst, const float* src, size_t n, cudaStream_t s);

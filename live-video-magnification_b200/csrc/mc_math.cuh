@@ -220,6 +220,59 @@ __device__ __forceinline__ void lab_to_bgr_fast(float L, float a, float b, const
 }
 #endif
 
+// ------------------------------------------------------------------------------------------------
+// Front of the reference chain: GrayscaleProcessor and PreprocessProcessor arithmetic,
+// restated from OpenCV's u8 paths and checked bit-exact against cv2 on the CPU (tests/test_host.py).
+// ------------------------------------------------------------------------------------------------
+// cv::cvtColor(COLOR_BGR2GRAY) on u8 (GrayscaleProcessor.cpp:13): 15-bit fixed point, round to nearest.
+MC_HD uint8_t bgr_to_gray_u8(int b, int g, int r) { return (uint8_t)((b * 3735 + g * 19235 + r * 9798 + 16384) >> 15); }
+
+#if defined(__CUDA_ARCH__)
+#define MC_FMUL(a, b) __fmul_rn((a), (b))
+#define MC_FADD(a, b) __fadd_rn((a), (b))
+#define MC_RINT_I(x) __float2int_rn(x)
+#else
+#define MC_FMUL(a, b) ((a) * (b))      // host build uses -ffp-contract=off
+#define MC_FADD(a, b) ((a) + (b))
+#define MC_RINT_I(x) ((int)lrintf(x))
+#endif
+
+struct AreaTap { int di, si; float alpha; };   // OpenCV's DecimateAlpha: destination index, source index, weight
+
+// cv::resize(INTER_AREA) for u8 (PreprocessProcessor.cpp:42), one output sample (dy, dx, channel ch).
+//  * integer scale on both axes ("area fast"): 2x2 -> (sum + 2) >> 2 ; otherwise rint(int_sum * (1.f / area))
+//  * otherwise: per contributing source row a float row sum  buf = sum_k S * alpha_k  (sequential, no FMA),
+//    accumulated over rows as  sum = beta * buf  /  sum += beta * buf ; result rint(sum), saturated.
+// xtab / ytab list the taps grouped by destination index; xofs[dx] .. xofs[dx+1] are dx's taps.
+MC_HD uint8_t resize_area_sample(const uint8_t* __restrict__ src, size_t step, int cn, int ch, int dy, int dx,
+                                 int iscale_x, int iscale_y, bool area_fast, const AreaTap* __restrict__ xtab,
+                                 const int* __restrict__ xofs, const AreaTap* __restrict__ ytab,
+                                 const int* __restrict__ yofs) {
+    if (area_fast) {
+        int sum = 0;
+        for (int sy = 0; sy < iscale_y; ++sy) {
+            const uint8_t* row = src + (size_t)(dy * iscale_y + sy) * step + (size_t)(dx * iscale_x) * cn + ch;
+            for (int sx = 0; sx < iscale_x; ++sx) sum += row[(size_t)sx * cn];
+        }
+        if (iscale_x == 2 && iscale_y == 2) return (uint8_t)((sum + 2) >> 2);
+        const float scale = 1.f / (float)(iscale_x * iscale_y);
+        int v = MC_RINT_I(MC_FMUL((float)sum, scale));
+        return (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+    }
+    float sum = 0.f;
+    bool first = true;
+    for (int j = yofs[dy]; j < yofs[dy + 1]; ++j) {
+        const uint8_t* row = src + (size_t)ytab[j].si * step + ch;
+        float buf = 0.f;
+        for (int k = xofs[dx]; k < xofs[dx + 1]; ++k) buf = MC_FADD(buf, MC_FMUL((float)row[(size_t)xtab[k].si * cn], xtab[k].alpha));
+        const float t = MC_FMUL(ytab[j].alpha, buf);
+        sum = first ? t : MC_FADD(sum, t);
+        first = false;
+    }
+    int v = MC_RINT_I(sum);
+    return (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+}
+
 // iirFilter (TemporalFilter.cpp:9-22): cv::addWeighted rounds once from a double sum.
 MC_HD float ema(float state, float x, double one_minus_c, double c) {
     return (float)((double)state * one_minus_c + (double)x * c);

@@ -144,6 +144,39 @@ void motion_gains(double amplification, double coWavelength, int levels, int w, 
     }
 }
 
+// OpenCV computeResizeAreaTab (imgproc/resize.cpp): taps of the general INTER_AREA path along one axis,
+// grouped by destination index; ofs[d] .. ofs[d+1] index d's taps.
+void build_area_tab(int ssize, int dsize, double scale, std::vector<AreaTap>& tab, std::vector<int>& ofs) {
+    tab.clear();
+    ofs.assign((size_t)dsize + 1, 0);
+    for (int dx = 0; dx < dsize; ++dx) {
+        ofs[(size_t)dx] = (int)tab.size();
+        const double fsx1 = dx * scale, fsx2 = fsx1 + scale;
+        const double cell = std::min(scale, ssize - fsx1);
+        int sx1 = (int)std::ceil(fsx1), sx2 = (int)std::floor(fsx2);
+        sx2 = std::min(sx2, ssize - 1);
+        sx1 = std::min(sx1, sx2);
+        if (sx1 - fsx1 > 1e-3) tab.push_back(AreaTap{dx, sx1 - 1, (float)((sx1 - fsx1) / cell)});
+        for (int sx = sx1; sx < sx2; ++sx) tab.push_back(AreaTap{dx, sx, (float)(1.0 / cell)});
+        if (fsx2 - sx2 > 1e-3) tab.push_back(AreaTap{dx, sx2, (float)(std::min(std::min(fsx2 - sx2, 1.), cell) / cell)});
+    }
+    ofs[(size_t)dsize] = (int)tab.size();
+}
+
+// PreprocessProcessor.cpp:20-33: normalised ROI -> pixel rectangle clamped inside the frame (>= 1 px).
+void preprocess_roi(int cols, int rows, bool enabled, float rx, float ry, float rw, float rh, int& x, int& y, int& w, int& h) {
+    x = 0; y = 0; w = cols; h = rows;
+    if (!enabled) return;
+    x = (int)std::lround((double)rx * cols);
+    y = (int)std::lround((double)ry * rows);
+    w = (int)std::lround((double)rw * cols);
+    h = (int)std::lround((double)rh * rows);
+    x = std::min(std::max(x, 0), cols - 1);
+    y = std::min(std::max(y, 0), rows - 1);
+    w = std::min(std::max(w, 1), cols - x);
+    h = std::min(std::max(h, 1), rows - y);
+}
+
 void gaussian_kernel_13_3(float taps[13]) {
     // cv::getGaussianKernel(13, 3.0, CV_32F): exp(-x^2/(2 sigma^2)) normalised in double, then narrowed.
     double t[13], sum = 0.0;

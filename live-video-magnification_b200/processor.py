@@ -21,7 +21,7 @@ import numpy as np
 from . import capi
 from .capi import McParams, MagcoreError
 
-__all__ = ["MagnificationMode", "MagnificationParams", "PreprocessParams", "ProcessorConfig", "Frame",
+__all__ = ["ProcessingChainB200", "MagnificationMode", "MagnificationParams", "PreprocessParams", "ProcessorConfig", "Frame",
            "IProcessor", "MagnificationProcessor", "toParams", "MagUiValues", "calculateMaxLevels",
            "getOptimalBufferSize", "butterworth", "MagcoreError"]
 
@@ -260,3 +260,51 @@ class MagnificationProcessor(IProcessor):
         a = np.empty((self.lanes, h, w, c), np.float32)
         self._check(self._lib.mc_get_float_output(self._h, a.ctypes.data, a.size))
         return a
+
+
+class ProcessingChainB200:
+    """The reference's per-frame chain ``runChainOnce(chain, in, cfg, original)`` (reference
+    src/processing/ChainBuilder.cpp:11-29: PreprocessProcessor -> GrayscaleProcessor -> MagnificationProcessor)
+    executed on the B200 behind ``mc_chain_process``: the raw frame is uploaded once, ROI crop + INTER_AREA
+    downscale and BGR2GRAY run bit-exact on the device, the magnification core runs on their result.
+
+    ``run_chain_once(frame, cfg) -> (cur, original)`` returns the *same* frame object wherever the reference
+    returns the same FrameRef (identity stages / passthrough)."""
+
+    def __init__(self, device: int = 0):
+        self.magnifier = MagnificationProcessor(device=device, lanes=1)
+
+    def reset(self) -> None:
+        """ProcessingChain's recovery path resets every stage (ProcessingChain.cpp:50-62); only the magnifier has state."""
+        self.magnifier.reset()
+
+    def run_chain_once(self, frame: Frame, cfg: ProcessorConfig):
+        m = self.magnifier
+        p = _to_mc(cfg)
+        info = capi.McChainInfo()
+        img = frame.image
+        if img is None or img.size == 0:
+            m._check(m._lib.mc_chain_process(m._h, None, 0, 0, 3, 0, C.byref(p), int(cfg.grayscale), None, 0, None, 0, C.byref(info)))
+            return frame, frame
+        if img.dtype != np.uint8:
+            raise TypeError("image must be uint8")
+        img = img if img.flags["C_CONTIGUOUS"] else np.ascontiguousarray(img)
+        h, w = img.shape[:2]
+        c = 1 if img.ndim == 2 else img.shape[2]
+        out = np.empty(h * w * c, np.uint8)
+        orig = np.empty(h * w * c, np.uint8)
+        m._check(m._lib.mc_chain_process(m._h, img.ctypes.data, w, h, c, w * c, C.byref(p), int(cfg.grayscale), out.ctypes.data,
+                                         out.size, orig.ctypes.data, orig.size, C.byref(info)))
+
+        def view(buf, ww, hh, cc):
+            a = buf[:ww * hh * cc]
+            return a.reshape(hh, ww).copy() if cc == 1 else a.reshape(hh, ww, cc).copy()
+
+        original = frame if info.orig_is_input else replace(
+            frame, image=view(orig, info.orig_w, info.orig_h, info.orig_channels), width=info.orig_w, height=info.orig_h)
+        if info.cur_is_input:
+            cur = frame
+        else:
+            cur = replace(frame, image=view(out, info.out_w, info.out_h, info.out_channels), width=info.out_w,
+                          height=info.out_h, format="BGR8" if info.out_channels == 3 else "Gray8")
+        return cur, original

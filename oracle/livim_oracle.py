@@ -802,3 +802,55 @@ class MagnificationProcessor:
         if not produced:  # :61
             return False, image
         return True, out
+
+
+# --------------------------------------------------------------------------------------------------
+# Front of the chain: PreprocessProcessor.cpp, GrayscaleProcessor.cpp, ChainBuilder.cpp
+# --------------------------------------------------------------------------------------------------
+def _lround(x: float) -> int:
+    """std::lround: half away from zero."""
+    return int(math.floor(abs(x) + 0.5)) * (1 if x >= 0 else -1)
+
+
+def preprocess(image: np.ndarray, cfg: ProcessorConfig):
+    """PreprocessProcessor::process (PreprocessProcessor.cpp:10-51). Returns (changed, image)."""
+    if image is None or image.size == 0:
+        return False, image
+    p = cfg.preprocess
+    divisor = min(max(p.downscale, 1), 8)
+    if not p.roiEnabled and divisor == 1:
+        return False, image
+    rows, cols = image.shape[:2]
+    x, y, w, h = 0, 0, cols, rows
+    if p.roiEnabled:
+        f = lambda v: float(np.float32(v))   # the reference stores the ROI as float
+        x, y = _lround(f(p.roiX) * cols), _lround(f(p.roiY) * rows)
+        w, h = _lround(f(p.roiW) * cols), _lround(f(p.roiH) * rows)
+        x = min(max(x, 0), cols - 1); y = min(max(y, 0), rows - 1)
+        w = min(max(w, 1), cols - x); h = min(max(h, 1), rows - y)
+    cropped = image[y:y + h, x:x + w]
+    if divisor > 1:
+        dw, dh = max(1, cropped.shape[1] // divisor), max(1, cropped.shape[0] // divisor)
+        out = cv2.resize(np.ascontiguousarray(cropped), (dw, dh), interpolation=cv2.INTER_AREA)
+    else:
+        out = cropped.copy()
+    return True, out
+
+
+def grayscale(image: np.ndarray, cfg: ProcessorConfig):
+    """GrayscaleProcessor::process (GrayscaleProcessor.cpp:7-16). Returns (changed, image)."""
+    if not cfg.grayscale or image is None or image.size == 0 or image.ndim == 2:
+        return False, image
+    return True, cv2.cvtColor(image, cv2.COLOR_BGR2GRAY)
+
+
+def run_chain_once(magnifier: "MagnificationProcessor", image: np.ndarray, cfg: ProcessorConfig):
+    """runChainOnce (ChainBuilder.cpp:19-29): Preprocess -> Grayscale -> Magnification; returns
+    (cur, original, cur_is_input, original_is_input)."""
+    pre_changed, cur = preprocess(image, cfg)
+    original = cur
+    gray_changed, cur = grayscale(cur, cfg)
+    produced, out = magnifier.process(cur, cfg)
+    if produced:
+        cur = out
+    return cur, original, not (pre_changed or gray_changed or produced), not pre_changed

@@ -24,12 +24,12 @@ def hc(built):
 def test_library_exports_every_declared_symbol(built):
     hdr = open(os.path.join(ROOT, "include", "magcore_b200.h")).read()
     declared = set(re.findall(r"\b(mc_[a-z_0-9]+)\s*\(", hdr))
-    declared -= {"mc_status", "mc_mode", "mc_params", "mc_handle"}
+    declared -= {"mc_status", "mc_mode", "mc_params", "mc_handle", "mc_chain_info"}
     lib = C.CDLL(built[0])
     missing = [s for s in sorted(declared) if not hasattr(lib, s)]
     assert not missing, missing
     assert declared == set(capi.SIGNATURES), declared ^ set(capi.SIGNATURES)
-    assert lib.mc_abi_version() == 1
+    assert lib.mc_abi_version() == 2
 
 
 def test_no_cpu_fallback_without_gpu(built):
@@ -152,3 +152,30 @@ def test_cpp_adapter_compiles_and_refuses_without_gpu(built):
         assert r.returncode == 0 and "OK gpu" in r.stdout, r.stdout
     else:
         assert r.returncode == 3 and "no usable CUDA device" in r.stdout, r.stdout
+
+
+def test_front_stage_arithmetic_is_bit_exact_with_cv2(hc):
+    """the product's BGR2GRAY and INTER_AREA per-sample functions (mc_math.cuh) and the tap/ROI
+    builders (mc_tables.cpp), compiled for the CPU, against cv2 — integer-scale and fractional-scale paths."""
+    rng = np.random.default_rng(5)
+    px = rng.integers(0, 256, (200000, 3), dtype=np.uint8)
+    g = np.empty(len(px), np.uint8)
+    hc.hc_bgr2gray(px.ctypes.data_as(C.c_void_p), len(px), g.ctypes.data_as(C.c_void_p))
+    assert np.array_equal(g, cv2.cvtColor(px[None], cv2.COLOR_BGR2GRAY)[0])
+    for c in (1, 3):
+        for (h, w, d) in ((50, 67, 2), (101, 77, 3), (37, 91, 4), (135, 241, 7), (64, 100, 8), (33, 35, 2), (90, 121, 5),
+                          (48, 64, 2), (51, 69, 3), (64, 96, 4), (540, 960, 8), (270, 480, 5), (7, 9, 8), (216, 383, 2), (60, 60, 6)):
+            dw, dh = max(1, w // d), max(1, h // d)
+            src = rng.integers(0, 256, (h, w, c) if c > 1 else (h, w), dtype=np.uint8)
+            ref = cv2.resize(src, (dw, dh), interpolation=cv2.INTER_AREA)
+            dst = np.empty_like(ref)
+            hc.hc_resize_area(src.ctypes.data_as(C.c_void_p), h, w, c, dw, dh, dst.ctypes.data_as(C.c_void_p))
+            assert np.array_equal(dst, ref), (c, h, w, d)
+    out = (C.c_int * 4)()
+    for (cols, rows, rx, ry, rw, rh) in ((1920, 1080, 0.25, 0.25, 0.5, 0.5), (640, 480, 0.1, 0.9, 0.95, 0.5), (333, 77, 0.0, 0.0, 1.0, 1.0),
+                                          (100, 100, 0.995, 0.5, 0.2, 0.001), (1919, 1079, 0.3333, 0.6667, 0.3333, 0.25)):
+        hc.hc_roi(cols, rows, 1, C.c_float(rx), C.c_float(ry), C.c_float(rw), C.c_float(rh), out)
+        cfg = O.ProcessorConfig(preprocess=O.PreprocessParams(1, True, rx, ry, rw, rh))
+        img = np.zeros((rows, cols), np.uint8)
+        _, cropped = O.preprocess(img, cfg)
+        assert (out[2], out[3]) == (cropped.shape[1], cropped.shape[0]), (cols, rows, list(out))
