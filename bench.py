@@ -9,8 +9,9 @@
 A *step* = one frame for each of `lanes` independent 1920x1080x3 streams (one launch set of the
 lane-batched kernels).  `value` = frames/s with frames resident in HBM; `e2e` = the same metric
 through the public host API (pinned host frames in, pinned host frames out, copies inside the
-timed region).  `--impl reference` times the CPU oracle (the reference's OpenCV path restated on
-cv2, all host threads) on the same workload.
+timed region).  `--impl reference` times the reference's own CPU implementation of the path (its sources
+compiled in place into oracle/_ref, OpenCV kernels through cv2, all host threads; the oracle restatement if that
+module is absent) on the same workload.
 """
 import argparse
 import ctypes as C
@@ -126,22 +127,38 @@ def oracle_cfg():
                                                           UI["low"], UI["high"], UI["chroma"], UI["levels"], UI["fps"]))
 
 
+def cpu_arm():
+    """The CPU arm: the reference's own sources compiled in place (oracle/_ref/_livim_ref, OpenCV kernels through
+    cv2) when that module is present — kind "reference" — else the oracle restatement — kind "port".
+    -> (process(frame) callable, kind, description)."""
+    import cv2
+    O, ocfg = oracle_cfg()
+    from oracle import livim_ref
+    R = livim_ref.load()
+    if R is not None:
+        rcfg = livim_ref.to_ref_config(R, ocfg)
+        proc = R.Processor()
+        return (lambda f: proc.process(f, rcfg)), "reference", \
+            f"reference src/processing compiled in place (oracle/_ref), OpenCV {cv2.__version__} kernels via cv2"
+    proc = O.MagnificationProcessor()
+    return (lambda f: proc.process(f, ocfg)), "port", f"cv2 {cv2.__version__} oracle restatement"
+
+
 def time_oracle(n_warm, n_frames):
-    """CPU baseline: the oracle (cv2, all host threads) on frames of the same workload -> frames/s."""
+    """CPU baseline on frames of the same workload, all host threads -> (frames/s, cores, seconds, kind, what)."""
     import cv2
     from lvm_b200.synth import synth_frame
-    O, cfg = oracle_cfg()
+    process, kind, what = cpu_arm()
     cores = os.cpu_count() or 1
     cv2.setNumThreads(cores)
     frames = [synth_frame(t, W, H, CH) for t in range(8)]
-    proc = O.MagnificationProcessor()
     for t in range(n_warm):
-        proc.process(frames[t % 8], cfg)
+        process(frames[t % 8])
     t0 = time.perf_counter()
     for t in range(n_frames):
-        proc.process(frames[(n_warm + t) % 8], cfg)
+        process(frames[(n_warm + t) % 8])
     dt = time.perf_counter() - t0
-    return n_frames / dt, cores, dt
+    return n_frames / dt, cores, dt, kind, what
 
 
 def run_reference(args, rank, world):
@@ -150,26 +167,25 @@ def run_reference(args, rank, world):
     per_step = args.ref_frames_per_step
     import cv2
     from lvm_b200.synth import synth_frame
-    O, cfg = oracle_cfg()
+    process, kind, what = cpu_arm()
     cores = os.cpu_count() or 1
     cv2.setNumThreads(cores)
     frames = [synth_frame(t, W, H, CH) for t in range(8)]
-    proc = O.MagnificationProcessor()
     i = 0
     for _ in range(args.warmup * per_step):
-        proc.process(frames[i % 8], cfg); i += 1
+        process(frames[i % 8]); i += 1
     t0 = time.perf_counter()
     for _ in range(args.steps * per_step):
-        proc.process(frames[i % 8], cfg); i += 1
+        process(frames[i % 8]); i += 1
     dt = time.perf_counter() - t0
     fps = args.steps * per_step / dt
-    sample = f"{args.steps} steps x {per_step} frames of the 1080p workload, cv2 {cv2.__version__}, {cores} threads"
+    sample = f"{args.steps} steps x {per_step} frames of the 1080p workload, {what}, {cores} threads"
     return json.dumps({
         "impl": "reference", "metric": "1080p frames/sec (Laplace, 6-level)", "value": fps, "unit": "frames/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "frames_per_step": per_step},
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     })
@@ -340,9 +356,9 @@ def run_ours(args, rank, world, local_rank):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, cores, dt = time_oracle(2, args.cpu_frames)
-        cpu = {"value": v, "unit": "frames/s", "cores": cores, "kind": "port",
-               "sample": f"{args.cpu_frames} frames of the same 1080p clip through the cv2 oracle ({dt:.1f} s)"}
+        v, cores, dt, kind, what = time_oracle(2, args.cpu_frames)
+        cpu = {"value": v, "unit": "frames/s", "cores": cores, "kind": kind,
+               "sample": f"{args.cpu_frames} frames of the same 1080p clip through the {what} ({dt:.1f} s)"}
 
     line = None
     if rank == 0:

@@ -14,17 +14,25 @@ tschnz/Live-Video-Magnification behind ``MagnificationProcessor::process``:
 Every function cites the reference file:line it follows. Only ``tests/``, ``__graft_entry__.smoke()``
 and ``bench.py``'s cpu_baseline / ``--impl reference`` legs may import this module.
 
-PARITY PIN STATUS: the reference ships no tests, golden vectors or fixtures for this path
- and cannot be compiled here (no OpenCV C++ headers, no Qt).  The arithmetic of the
-path lives in third-party OpenCV 4 (vcpkg port ``opencv4``, version pinned only indirectly by the
-vcpkg baseline ``a5ac4c37…`` in vcpkg.json:6).  This oracle therefore executes *the same OpenCV
-kernels* through ``cv2`` (opencv-python-headless 4.13.0) in the reference's call order — it is pinned
-to OpenCV itself, not to reference-owned vectors: "parity unpinned by the reference".
-``tests/golden/*.npz`` freeze this oracle's outputs (with cv2.__version__) so drift is detectable.
+PARITY PIN STATUS: the reference ships no tests, golden vectors or fixtures for this path (SURVEY.md §4,
+§8c), and its CMake/vcpkg build cannot run here (no OpenCV C++ headers or libraries, no Qt).  The oracle is
+pinned against OUTPUTS OF THE REFERENCE ITSELF RUN HERE instead: ``oracle/build_ref.py`` compiles the reference's
+own hot-path sources where they lie (/root/reference/src/processing/**, unmodified) against ``oracle/cvshim`` —
+an OpenCV-shaped facade that forwards every pixel operation to the real OpenCV 4.13 kernels in ``cv2`` — into
+``oracle/_ref/_livim_ref``; ``tests/test_ref_pin.py`` requires this restatement to reproduce the compiled
+reference BIT FOR BIT (u8 outputs, passthrough decisions, float temporal state of all three modes, the front
+of the chain, and the host functions), and ``tests/golden/*.npz`` are outputs of that compiled reference
+(generator: tests/golden/make_golden.py).  What remains outside the pin, because cv2 cannot execute it, is
+stated in oracle/cvshim/opencv2/core.hpp: ``Mat::convertTo`` and the MatExpr-to-OpenCV-call lowering are
+restated from OpenCV's documented behaviour in both the facade and this file; and the OpenCV *version* is the
+wheel's 4.13.0, not whatever the reference's vcpkg baseline (``a5ac4c37…``, vcpkg.json:6) resolves to.
 """
 from __future__ import annotations
 
+import ctypes
 import math
+import os
+import subprocess
 from dataclasses import dataclass, field, replace
 from typing import List, Optional, Tuple
 
@@ -32,6 +40,33 @@ import cv2
 import numpy as np
 
 F32 = np.float32
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIBM = None
+
+
+def _libm():
+    """glibc acosf / cosf / sinf as the reference calls them (oracle/libm_f32.c), built on first use with gcc
+    into oracle/_ref/ (numpy's float32 ufuncs differ from libm in the last ulp on about a third of samples)."""
+    global _LIBM
+    if _LIBM is None:
+        src, out = os.path.join(_HERE, "libm_f32.c"), os.path.join(_HERE, "_ref", "libm_f32.so")
+        if not os.path.exists(out) or os.path.getmtime(out) < os.path.getmtime(src):
+            os.makedirs(os.path.dirname(out), exist_ok=True)
+            tmp = out + f".{os.getpid()}.tmp"
+            subprocess.run(["gcc", "-O2", "-shared", "-fPIC", src, "-o", tmp, "-lm"], check=True)
+            os.replace(tmp, out)
+        lib = ctypes.CDLL(out)
+        fp = ctypes.POINTER(ctypes.c_float)
+        lib.livim_arccos_f32.argtypes = [fp, fp, ctypes.c_size_t]
+        lib.livim_cossin_f32.argtypes = [fp, fp, fp, ctypes.c_size_t]
+        lib.livim_arccos_f32.restype = lib.livim_cossin_f32.restype = None
+        _LIBM = lib
+    return _LIBM
+
+
+def _fptr(a: np.ndarray):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
 
 # --------------------------------------------------------------------------------------------------
 # IProcessor.hpp:10-48 — parameter structs
@@ -413,12 +448,19 @@ def _filter2d(img, k):
 
 
 def arc_cos(x: np.ndarray) -> np.ndarray:
-    """RieszPyramid.cpp:8-23 — note the clamp returns -1.0/+1.0 *radians* (quirk)."""
-    with np.errstate(invalid="ignore"):
-        r = np.arccos(x).astype(F32)  # NaN input -> acosf(NaN) = NaN in both
-    r = np.where(x < -1.0, F32(-1.0), r)
-    r = np.where(x > 1.0, F32(1.0), r)
-    return r.astype(F32)
+    """RieszPyramid.cpp:8-23 (libm acosf) — note the clamp returns -1.0/+1.0 *radians* (quirk)."""
+    x = np.ascontiguousarray(x, dtype=F32)
+    out = np.empty_like(x)
+    _libm().livim_arccos_f32(_fptr(x), _fptr(out), x.size)
+    return out
+
+
+def cos_sin(x: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+    """RieszPyramid.cpp:25-38 (libm cosf / sinf)."""
+    x = np.ascontiguousarray(x, dtype=F32)
+    c, s_ = np.empty_like(x), np.empty_like(x)
+    _libm().livim_cossin_f32(_fptr(x), _fptr(c), _fptr(s_), x.size)
+    return c, s_
 
 
 def _patch_nans(m: np.ndarray) -> np.ndarray:
@@ -494,7 +536,7 @@ class RieszLevel:
             mag_v = cv2.sqrt(cv2.add(cv2.multiply(tc, tc), cv2.multiply(ts, ts)))
             mag_v2 = _scale(mag_v, alpha)
             _, mag_v2 = cv2.threshold(mag_v2, threshold, 0, cv2.THRESH_TRUNC)
-            pc, ps = np.cos(mag_v2).astype(F32), np.sin(mag_v2).astype(F32)
+            pc, ps = cos_sin(mag_v2)
             pair = cv2.add(cv2.multiply(self.rx, tc), cv2.multiply(self.ry, ts))
             pair = _patch_nans(cv2.divide(pair, mag_v))
             self.lowpass = cv2.subtract(cv2.multiply(self.lowpass, pc), cv2.multiply(pair, ps))

@@ -23,7 +23,8 @@ def test_reference_arm_prints_one_json_line():
     assert d["value"] > 0 and d["e2e"]["value"] == d["value"]
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
+    from oracle import livim_ref
+    assert cb["kind"] == ("reference" if livim_ref.load() is not None else "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
     assert "workload" in d["config"]
 
 
