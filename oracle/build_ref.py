@@ -31,7 +31,9 @@ REF_UNITS = [
     "processing/GrayscaleProcessor.cpp",
     "processing/ChainBuilder.cpp",
 ]
-OWN_UNITS = [os.path.join(HERE, "cvshim", "cvshim.cpp"), os.path.join(HERE, "ref_binding.cpp")]
+OWN_UNITS = [os.path.join(HERE, "cvshim", "cvshim.cpp"), os.path.join(HERE, "ref_binding.cpp"), os.path.join(HERE, "mc_dl.cpp")]
+ROOT = os.path.dirname(HERE)
+ADAPTER_INC = [os.path.join(ROOT, "live-video-magnification_b200", "adapter"), os.path.join(ROOT, "include")]
 
 
 def module_path() -> str:
@@ -50,13 +52,14 @@ def build(force: bool = False) -> str | None:
     import pybind11
 
     srcs = [os.path.join(REF_SRC, u) for u in REF_UNITS] + OWN_UNITS
-    deps = srcs + [os.path.join(HERE, "cvshim", "opencv2", h) for h in ("core.hpp", "imgproc.hpp")] + [__file__]
+    deps = srcs + [os.path.join(HERE, "cvshim", "opencv2", h) for h in ("core.hpp", "imgproc.hpp")] + [__file__] + \
+        [os.path.join(ADAPTER_INC[0], "MagnificationProcessorB200.hpp"), os.path.join(ADAPTER_INC[1], "magcore_b200.h")]
     if not force and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in deps):
         return out
     obj_dir = os.path.join(OUT_DIR, "obj")
     os.makedirs(obj_dir, exist_ok=True)
     flags = ["-O2", "-std=c++20", "-fPIC", "-fvisibility=hidden", "-I", os.path.join(HERE, "cvshim"), "-I", REF_SRC,
-             "-I", pybind11.get_include(), "-I", sysconfig.get_paths()["include"]]
+             "-I", pybind11.get_include(), "-I", sysconfig.get_paths()["include"], "-I", ADAPTER_INC[0], "-I", ADAPTER_INC[1]]
 
     def compile_one(src: str) -> str:
         obj = os.path.join(obj_dir, os.path.basename(src).replace(".cpp", ".o"))
@@ -71,7 +74,7 @@ def build(force: bool = False) -> str | None:
 
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 2)) as ex:
         objs = list(ex.map(compile_one, srcs))
-    r = subprocess.run(["g++", "-shared", "-o", out, *objs], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    r = subprocess.run(["g++", "-shared", "-o", out, *objs, "-ldl"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout)
         raise RuntimeError("oracle/_ref: link failed")

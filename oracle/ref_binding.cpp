@@ -15,7 +15,9 @@
 
 #include "core/Frame.hpp"
 #include "processing/ChainBuilder.hpp"
+#include "processing/GrayscaleProcessor.hpp"
 #include "processing/IProcessor.hpp"
+#include "processing/PreprocessProcessor.hpp"
 #include "processing/MagnificationParamsUi.hpp"
 #include "processing/MagnificationProcessor.hpp"
 #include "processing/magnification/MagnifyCore.hpp"
@@ -26,6 +28,10 @@ namespace py = pybind11;
 using namespace livim;
 
 namespace cv { void cvshim_selfcheck(); }
+void mc_dl_open(const std::string& path);   // oracle/mc_dl.cpp
+
+// the reference-side adapter of the product, compiled here against the REAL reference headers
+#include "MagnificationProcessorB200.hpp"
 
 static cv::Mat mat_from_u8(const py::array& arr_in) {
     py::array_t<uint8_t, py::array::c_style | py::array::forcecast> arr(arr_in);
@@ -69,6 +75,30 @@ struct RefChain {
         FrameRef original;
         FrameRef out = runChainOnce(chain, in, cfg, original);
         if (out->seq != in->seq || out->ptsUs != in->ptsUs) throw std::runtime_error("frame metadata not preserved");
+        return py::make_tuple(mat_to_np(out->image), mat_to_np(original->image), out.get() == in.get(), original.get() == in.get(),
+                              out->format == PixelFormat::Gray8);
+    }
+    void reset() { for (auto& p : chain) p->reset(); }
+};
+
+// The drop-in itself: the reference's chain exactly as buildProcessors() assembles it (ChainBuilder.cpp:11-17) with
+// the single substitution INTEGRATION.md describes at ChainBuilder.cpp:15 — MagnificationProcessorB200 (the adapter
+// over the C ABI) in place of MagnificationProcessor — driven by the reference's own runChainOnce().  The two
+// front stages are the reference's compiled code.  Needs a B200: the adapter's constructor throws without one.
+struct DropInChain {
+    std::vector<std::unique_ptr<IProcessor>> chain;
+    std::uint64_t seq = 0;
+    explicit DropInChain(int device) {
+        chain.push_back(std::make_unique<PreprocessProcessor>());
+        chain.push_back(std::make_unique<GrayscaleProcessor>());
+        chain.push_back(std::make_unique<MagnificationProcessorB200>(device));
+    }
+    py::tuple process(const py::array& frame, const ProcessorConfig& cfg) {
+        FrameRef in = frame_from_np(frame, seq++);
+        FrameRef original;
+        FrameRef out = runChainOnce(chain, in, cfg, original);
+        if (out->seq != in->seq || out->ptsUs != in->ptsUs) throw std::runtime_error("frame metadata not preserved");
+        if (out.get() != in.get() && out->image.data == in->image.data) throw std::runtime_error("output aliases the input buffer");
         return py::make_tuple(mat_to_np(out->image), mat_to_np(original->image), out.get() == in.get(), original.get() == in.get(),
                               out->format == PixelFormat::Gray8);
     }
@@ -200,6 +230,8 @@ PYBIND11_MODULE(_livim_ref, m) {
         return py::make_tuple(a, b);
     });
 
+    m.def("set_magcore_library", &mc_dl_open, "path of libmagcore_b200.so for DropInChain (resolved lazily with dlopen)");
+    py::class_<DropInChain>(m, "DropInChain").def(py::init<int>()).def("process", &DropInChain::process).def("reset", &DropInChain::reset);
     py::class_<RefChain>(m, "Chain").def(py::init<>()).def("process", &RefChain::process).def("reset", &RefChain::reset);
     py::class_<RefProcessor>(m, "Processor").def(py::init<>()).def("process", &RefProcessor::process).def("reset", &RefProcessor::reset);
     py::class_<RefCore>(m, "Core")

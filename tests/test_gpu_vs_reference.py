@@ -72,3 +72,33 @@ def test_chain_vs_compiled_reference():
         rcur, rorig, _cur_same, _orig_same, _gray = rchain.process(f, rcfg)
         assert np.array_equal(orig.image, rorig), t                 # integer front stages: bit-exact
         assert cur.image.shape == rcur.shape and int(u8_diff(cur.image, rcur).max()) <= 1, t
+
+
+def test_dropin_chain_on_gpu():
+    """The drop-in as a maintainer would build it: the reference's PreprocessProcessor and GrayscaleProcessor
+    (compiled reference code), MagnificationProcessorB200 (the product's adapter, compiled against the real
+    reference headers) as the third stage, driven by the reference's runChainOnce — against the all-reference chain."""
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    R.set_magcore_library(os.path.join(root, "live-video-magnification_b200", "libmagcore_b200.so"))
+    for mode, ui, gray, pre in ((O.MODE_LAPLACE, (20, 50.0, 0.4, 3.0, 30, 4), False, (2, True, 0.1, 0.1, 0.8, 0.8)),
+                                (O.MODE_LAPLACE, (20, 50.0, 0.4, 3.0, 0, 3), True, (1, False, 0.0, 0.0, 1.0, 1.0)),
+                                (O.MODE_COLOR, (100, 0.0, 0.8, 1.2, 0, 2), False, (4, False, 0.0, 0.0, 1.0, 1.0)),
+                                (O.MODE_PHASE, (50, 50.0, 0.4, 3.0, 0, 3), False, (2, False, 0.0, 0.0, 1.0, 1.0))):
+        _, ocfg = make_cfgs(mode, *ui)
+        ocfg.grayscale = gray
+        ocfg.preprocess = O.PreprocessParams(*pre)
+        rcfg = livim_ref.to_ref_config(R, ocfg)
+        dropin, ref = R.DropInChain(0), R.Chain()
+        for t in range(8):
+            f = synth_frame(t, 640, 480, 3)
+            cur, orig, cur_is_in, orig_is_in, is_gray = dropin.process(f, rcfg)
+            rcur, rorig, rcur_is_in, rorig_is_in, ris_gray = ref.process(f, rcfg)
+            assert (cur_is_in, orig_is_in, is_gray) == (rcur_is_in, rorig_is_in, ris_gray), (mode, t)
+            assert np.array_equal(orig, rorig), (mode, t)
+            d = u8_diff(cur, rcur)
+            if mode == O.MODE_PHASE:
+                assert int(d.max()) <= 3 and float((d == 0).mean()) >= 0.995, (t, int(d.max()))
+            else:
+                assert int(d.max()) <= 1, (mode, t, int(d.max()))
+        dropin.reset()

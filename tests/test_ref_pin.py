@@ -227,3 +227,18 @@ def test_chain_bit_exact(extra):
         ocur, oorig, o_cur_is_in, o_orig_is_in = O.run_chain_once(omag, f, oc)
         assert r_cur_is_in == o_cur_is_in and r_orig_is_in == o_orig_is_in, t
         assert same(rorig, oorig) and same(rcur, ocur), t
+
+
+# --------------------------------------------------------------------------------------------------
+# The drop-in: reference chain + reference headers + the product's adapter (needs a B200 to run)
+# --------------------------------------------------------------------------------------------------
+def test_dropin_chain_builds_against_real_reference_headers_and_has_no_cpu_fallback(built):
+    """oracle/_ref/_livim_ref also holds the reference's chain with the ONE substitution of INTEGRATION.md
+    (MagnificationProcessorB200 at ChainBuilder.cpp:15), compiled against the reference's real IProcessor.hpp /
+    Frame.hpp.  Without a GPU constructing it must fail loudly: mc_create reports no device, the adapter throws."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: covered by tests/test_gpu_vs_reference.py::test_dropin_chain_on_gpu")
+    R.set_magcore_library(built[0])
+    with pytest.raises(RuntimeError, match="magcore_b200"):
+        R.DropInChain(0)
