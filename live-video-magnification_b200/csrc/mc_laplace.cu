@@ -20,6 +20,15 @@ namespace mc {
 namespace {
 
 // ---- TMA (cp.async.bulk.tensor) + mbarrier primitives -------------------------------------------
+#if defined(MC_CUDA_EMU)   // CPU logic emulation for GPU-less CI (tests/cuda_emu): same calls, emulated copy engine
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) { cuda_emu::mbar_init(bar, count); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) { cuda_emu::mbar_expect_tx(bar, bytes); }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) { cuda_emu::mbar_wait(bar, parity); }
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, int x, int y, int z, uint64_t* bar) {
+    const int c[3] = {x, y, z};
+    cuda_emu::tma_load(dst, tm, c, bar);
+}
+#else
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -43,6 +52,8 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, in
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
         ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z) : "memory");
 }
+
+#endif
 
 constexpr float kInv256 = 1.0f / 256.0f;
 constexpr float kInv64 = 1.0f / 64.0f;

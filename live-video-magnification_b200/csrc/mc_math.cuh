@@ -190,8 +190,13 @@ MC_HD void lab_to_bgr(float L, float a, float b, const LabInvCoeffs& k, const fl
 // (selects instead of branches), the [0,1] clip folded into saturating adds, and the gamma evaluated as
 // 1.055 * 2^(log2(v)/2.4) - 0.055 with lg2/ex2.approx.ftz; only when one of the three linear values is below
 // 8/1024 (where OpenCV's spline departs from the analytic curve) is the spline table consulted.
+#if defined(MC_CUDA_EMU)   // CPU logic emulation for GPU-less CI (tests/cuda_emu): libm instead of the SFU
+__device__ __forceinline__ float mc_lg2(float x) { return log2f(x); }
+__device__ __forceinline__ float mc_ex2(float x) { return exp2f(x); }
+#else
 __device__ __forceinline__ float mc_lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float mc_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+#endif
 
 __device__ __forceinline__ void lab_to_bgr_fast(float L, float a, float b, const LabInvCoeffs& k,
                                                 const float4* __restrict__ gtab, float& ob, float& og, float& orr) {

@@ -52,10 +52,14 @@ def _libm():
     if _LIBM is None:
         src, out = os.path.join(_HERE, "libm_f32.c"), os.path.join(_HERE, "_ref", "libm_f32.so")
         if not os.path.exists(out) or os.path.getmtime(out) < os.path.getmtime(src):
-            os.makedirs(os.path.dirname(out), exist_ok=True)
-            tmp = out + f".{os.getpid()}.tmp"
-            subprocess.run(["gcc", "-O2", "-shared", "-fPIC", src, "-o", tmp, "-lm"], check=True)
-            os.replace(tmp, out)
+            try:
+                os.makedirs(os.path.dirname(out), exist_ok=True)
+                tmp = out + f".{os.getpid()}.tmp"
+                subprocess.run(["gcc", "-O2", "-shared", "-fPIC", src, "-o", tmp, "-lm"], check=True)
+                os.replace(tmp, out)
+            except (OSError, subprocess.CalledProcessError):
+                if not os.path.exists(out):   # a prebuilt (possibly older-stamped) library is still the same code
+                    raise
         lib = ctypes.CDLL(out)
         fp = ctypes.POINTER(ctypes.c_float)
         lib.livim_arccos_f32.argtypes = [fp, fp, ctypes.c_size_t]

@@ -1,0 +1,77 @@
+"""Kernel-LOGIC regression on the CUDA-on-CPU emulation (tests/cuda_emu) — no GPU, no product library compute.
+
+The product's own kernel sources are compiled with g++ against an emulated CUDA runtime (CTA threads as cooperative
+fibers, emulated TMA / mbarrier / shuffles / cuFFT) into tests/cuda_emu/libmagcore_emu.so, and tiny clips of all
+three modes plus the fused front of the chain are checked against the oracle with the same tolerances as the
+`-m gpu` parity tests.  This catches indexing / border / staging / state-handling regressions in the kernels in
+the GPU-less container; it says nothing about performance or hardware behaviour — the `-m gpu` tests on a B200
+remain the parity gate.  The whole `-m gpu` suite can be pointed at the emulation with `MC_EMU=1` (tests/conftest.py).
+"""
+import numpy as np
+import pytest
+
+import lvm_b200 as L
+from lvm_b200 import capi
+from lvm_b200.synth import synth_frame
+from oracle import livim_oracle as O
+from common import make_cfgs, u8_diff
+
+pytestmark = pytest.mark.emu
+
+
+@pytest.fixture()
+def emu():
+    import conftest
+    saved = (capi.LIB_PATH, capi._lib)
+    conftest.use_emulated_library()
+    yield
+    capi.LIB_PATH, capi._lib = saved
+
+
+def run_mode(mode, ui, w, h, c, n, fps=30.0, options=()):
+    cfg, ocfg = make_cfgs(mode, *ui, fps)
+    proc, oproc = L.MagnificationProcessor(0), O.MagnificationProcessor()
+    for k, v in options:
+        proc.set_option(k, v)
+    worst, same = 0, []
+    for t in range(n):
+        f = synth_frame(t, w, h, c, fps=fps)
+        produced, out = proc.process_image(f, cfg)
+        oprod, oout = oproc.process(f, ocfg)
+        assert produced == oprod, t
+        if produced:
+            d = u8_diff(out, oout)
+            worst = max(worst, int(d.max()))
+            same.append(float((d == 0).mean()))
+    proc.close()
+    return worst, min(same)
+
+
+@pytest.mark.parametrize("w,h,c,levels,tma", [(131, 75, 3, 4, 1), (131, 75, 3, 4, 0), (96, 67, 1, 3, 1)])
+def test_laplace_kernels_on_emulation(emu, w, h, c, levels, tma):
+    worst, _ = run_mode(O.MODE_LAPLACE, (20, 50.0, 0.4, 3.0, 40, levels), w, h, c, 5, options=(("use_tma", tma),))
+    assert worst <= 1
+
+
+def test_color_kernels_on_emulation(emu):
+    worst, _ = run_mode(O.MODE_COLOR, (100, 0.0, 0.8, 1.2, 0, 2), 90, 66, 3, 19, fps=8.0)   # all DFT lengths 2..16 + wrap
+    assert worst <= 1
+
+
+def test_riesz_kernels_on_emulation(emu):
+    worst, same = run_mode(O.MODE_PHASE, (50, 50.0, 0.4, 3.0, 0, 3), 120, 90, 3, 5)
+    assert worst <= 3 and same >= 0.995
+
+
+def test_chain_front_stages_on_emulation(emu):
+    cfg, ocfg = make_cfgs(O.MODE_LAPLACE, 20, 50.0, 0.4, 3.0, 20, 3)
+    cfg.grayscale = ocfg.grayscale = True
+    cfg.preprocess = L.PreprocessParams(3, True, 0.1, 0.2, 0.77, 0.61)      # fractional INTER_AREA scale + ROI + gray
+    ocfg.preprocess = O.PreprocessParams(3, True, 0.1, 0.2, 0.77, 0.61)
+    chain, omag = L.ProcessingChainB200(0), O.MagnificationProcessor()
+    for t in range(3):
+        f = synth_frame(t, 203, 151, 3)
+        cur, orig = chain.run_chain_once(L.Frame(image=f, seq=t), cfg)
+        ocur, oorig, _, _ = O.run_chain_once(omag, f, ocfg)
+        assert np.array_equal(orig.image, oorig), t
+        assert int(u8_diff(cur.image, ocur).max()) <= 1, t

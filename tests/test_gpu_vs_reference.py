@@ -78,9 +78,8 @@ def test_dropin_chain_on_gpu():
     """The drop-in as a maintainer would build it: the reference's PreprocessProcessor and GrayscaleProcessor
     (compiled reference code), MagnificationProcessorB200 (the product's adapter, compiled against the real
     reference headers) as the third stage, driven by the reference's runChainOnce — against the all-reference chain."""
-    import os
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    R.set_magcore_library(os.path.join(root, "live-video-magnification_b200", "libmagcore_b200.so"))
+    from lvm_b200 import capi
+    R.set_magcore_library(capi.LIB_PATH)   # libmagcore_b200.so (tests/cuda_emu's build when MC_EMU=1)
     for mode, ui, gray, pre in ((O.MODE_LAPLACE, (20, 50.0, 0.4, 3.0, 30, 4), False, (2, True, 0.1, 0.1, 0.8, 0.8)),
                                 (O.MODE_LAPLACE, (20, 50.0, 0.4, 3.0, 0, 3), True, (1, False, 0.0, 0.0, 1.0, 1.0)),
                                 (O.MODE_COLOR, (100, 0.0, 0.8, 1.2, 0, 2), False, (4, False, 0.0, 0.0, 1.0, 1.0)),
