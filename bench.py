@@ -191,6 +191,51 @@ def run_reference(args, rank, world):
     })
 
 
+def kernel_table(prof, lanes):
+    """prof: {(kernel name, level): (launches, total ms)} from mc_profile_read -> (per-kernel table sorted by time share,
+    {kernel: ncu DRAM bytes per launch scaled to `lanes`} from profiles/traffic.json for captures that still apply)."""
+    px = level_pixels(W, H, LEVELS)
+    total_ms = sum(v[1] for v in prof.values())
+    table = []
+    for (name, lvl), (n, tms) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
+        # alg = this kernel's share of A_min (SURVEY 8d); io = bytes its interface forces through HBM
+        if name == "level" and lvl >= 1:
+            alg = 16 * CH * px[lvl] * lanes                       # two f32 state planes, read + write
+            io = alg + 4 * CH * (px[lvl] + px[lvl + 1]) * lanes    # + G_l read, G_{l+1} write (the band is not stored)
+        elif name in ("level", "down"):                           # level 0: Lab16 -> pyrDown -> G1
+            alg = 0
+            io = (2 * CH * px[0] + 4 * CH * px[1]) * lanes
+        elif name == "ingest_lab":                                # u8 -> Lab16 planes + G1
+            alg = CH * px[0] * lanes
+            io = alg + 2 * CH * px[0] * lanes + 4 * CH * px[1] * lanes
+        elif name == "lab16":
+            alg = CH * px[0] * lanes                              # u8 frame read
+            io = alg + 2 * CH * px[0] * lanes                     # + Lab16 write
+        elif name == "egress":
+            alg = CH * px[0] * lanes                              # u8 frame write
+            # + Lab16 read, hi_1/lo_1 read (band 1 rebuilt from state), cur_2 read
+            io = alg + (2 * CH * px[0] + 8 * CH * px[1] + (8 if LEVELS == 3 else 4) * CH * px[2]) * lanes
+        else:                                                     # collapse: hi_l/lo_l read, cur_l write, cur_{l+1} read
+            alg = 0
+            io = (12 * px[lvl] + (8 if lvl + 1 == LEVELS - 1 else 4) * px[lvl + 1]) * CH * lanes
+        us = tms / n * 1e3
+        table.append({"kernel": f"{name}[{lvl}]", "us_per_launch": us, "share": tms / total_ms,
+                      "algorithmic_GBps": alg / (us * 1e-6) / 1e9, "interface_GBps": io / (us * 1e-6) / 1e9,
+                      "interface_bytes": io})
+    # DRAM bytes per launch from the committed `ncu --set full` captures (profiles/traffic.json).  A capture only
+    # speaks for the kernel it was taken on: entries whose recorded interface model no longer matches the current
+    # kernel (e.g. after the band stopped being stored) are dropped -> traffic null until re-captured.
+    traffic = {}
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        model = {t["kernel"]: t["interface_bytes"] / lanes for t in table}
+        traffic = {k: (v["dram_read_bytes"] + v["dram_write_bytes"]) * lanes / v["lanes"] for k, v in tj.items()
+                   if k in model and abs(v.get("interface_bytes_per_lane", 0) - model[k]) <= 0.01 * model[k]}
+    except Exception:
+        pass
+    return table, traffic
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import lvm_b200 as L
@@ -303,41 +348,9 @@ def run_ours(args, rank, world, local_rank):
             step_dev(3 + i)
         prof = proc.profile_read()
         proc.set_option("profile_kernels", 0)
-        px = level_pixels(W, H, LEVELS)
-        total_ms = sum(v[1] for v in prof.values())
-        table = []
-        for (name, lvl), (n, tms) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
-            # alg = this kernel's share of A_min; io = bytes its interface forces through HBM
-            if name == "level" and lvl >= 1:
-                alg = 16 * CH * px[lvl] * lanes                       # two f32 state planes, read + write
-                io = alg + 4 * CH * (px[lvl] + px[lvl] + px[lvl + 1]) * lanes  # + G_l read, M_l write, G_{l+1} write
-            elif name in ("level", "down"):                           # level 0: Lab16 -> pyrDown -> G1
-                alg = 0
-                io = (2 * CH * px[0] + 4 * CH * px[1]) * lanes
-            elif name == "ingest_lab":                                # u8 -> Lab16 planes + G1
-                alg = CH * px[0] * lanes
-                io = alg + 2 * CH * px[0] * lanes + 4 * CH * px[1] * lanes
-            elif name == "lab16":
-                alg = CH * px[0] * lanes                              # u8 frame read
-                io = alg + 2 * CH * px[0] * lanes                     # + Lab16 write
-            elif name == "egress":
-                alg = CH * px[0] * lanes                              # u8 frame write
-                io = alg + (2 * CH * px[0] + 4 * CH * px[1] + 4 * CH * px[2]) * lanes
-            else:                                                     # collapse: M_l r+w, M_{l+1} read
-                alg = 0
-                io = (8 * px[lvl] + 4 * px[lvl + 1]) * CH * lanes
-            us = tms / n * 1e3
-            table.append({"kernel": f"{name}[{lvl}]", "us_per_launch": us, "share": tms / total_ms,
-                          "algorithmic_GBps": alg / (us * 1e-6) / 1e9, "interface_GBps": io / (us * 1e-6) / 1e9})
+        table, traffic = kernel_table(prof, lanes)
         dom = table[0]
         fused = next(t for t in table if t["kernel"] == "level[1]")   # the fused Laplace-pyramid + IIR kernel
-        # DRAM bytes per launch from the committed `ncu --set full` captures (profiles/traffic.json, 16 lanes)
-        traffic = {}
-        try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-            traffic = {k: (v["dram_read_bytes"] + v["dram_write_bytes"]) * lanes / v["lanes"] for k, v in tj.items()}
-        except Exception:
-            pass
         roof = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["algorithmic_GBps"], "peak": peak,
                 "unit": "GB/s", "frac": dom["algorithmic_GBps"] / peak, "traffic": traffic.get(dom["kernel"]),
                 "peak_source": peak_src, "interface_frac": dom["interface_GBps"] / peak,

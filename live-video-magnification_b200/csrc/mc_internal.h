@@ -92,14 +92,23 @@ cudaError_t launch_level(const LevelArgs& a, cudaStream_t s);
 // pure pyrDown of `a.g` into `a.g_next` (register/shuffle strip kernel; used when a.band == 0)
 cudaError_t launch_down(const LevelArgs& a, cudaStream_t s);
 
-// cur_l = pyrUp(cur_{l+1}) + m_l, in place in m_l (SpatialFilter.cpp:52-61)
-cudaError_t launch_collapse(const Level& lf, const Level& lc, float* m_fine, const float* m_coarse, int planes,
+// Where the synthesis kernels find a band: either a stored plane set (b == nullptr: value = a[i]) or the two
+// temporal-filter state plane sets of that level, from which the amplified band-pass is rebuilt on the fly as
+// gain * (a[i] - b[i]) = gain * (lowpassHi - lowpassLo) (TemporalFilter.cpp:21, MagnifyCore.hpp:127-134).
+struct BandSrc {
+    const float* a = nullptr;
+    const float* b = nullptr;
+    float gain = 1.0f;
+};
+
+// out_l = pyrUp(coarse) + fine (SpatialFilter.cpp:52-61); `out` may not alias the inputs
+cudaError_t launch_collapse(const Level& lf, const Level& lc, const BandSrc& fine, const BandSrc& coarse, float* out, int planes,
                             cudaStream_t s);
 
 // out = convert(input + chroma * pyrUp(pyrUp(c2) + m1)) (MagnifyCore.hpp:136-158).
-// m1 == nullptr: no motion; c2 == nullptr: cur_1 = m1.  C == 3 reads `lab`, C == 1 reads io.in.
+// m1.a == nullptr: no motion; c2.a == nullptr: cur_1 = m1.  C == 3 reads `lab`, C == 1 reads io.in.
 cudaError_t launch_egress(const FrameIO& io, const DeviceTables& tb, const int16_t* lab, int pitch16, size_t plane16,
-                          const float* m1, const Level& l1, const float* c2, const Level& l2, float chroma,
+                          const BandSrc& m1, const Level& l1, const BandSrc& c2, const Level& l2, float chroma,
                           float* float_out_or_null, cudaStream_t s);
 
 // PreprocessProcessor + GrayscaleProcessor on the device (mc_preprocess.cu)

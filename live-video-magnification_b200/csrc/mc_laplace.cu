@@ -561,19 +561,26 @@ __global__ void __launch_bounds__(32 * IG_WARPS) k_ingest_lab(const IngestArgs a
 }
 
 // ------------------------------------------------------------------------------------------------
-// collapse: cur_l = pyrUp(cur_{l+1}) + m_l, in place in m_l.  Tile 64 x 32, thread block 4 x 2 (same
-// register pyrUp as the level kernel), 128-bit accesses to m_l.
+// collapse: cur_l = pyrUp(cur_{l+1}) + m_l.  The band-passed, amplified band m_l = gain_l * (hi_l - lo_l)
+// (TemporalFilter.cpp:21, MagnifyCore.hpp:127-134) is not stored by the level kernel: it is rebuilt here
+// from the two state planes the level kernel has just written (same f32 subtract and multiply), which
+// takes 4 B/px off the HBM-bound level kernel's interface.  Tile 64 x 32, thread block 4 x 2 (same
+// register pyrUp as the level kernel), 128-bit accesses.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_collapse(Level lf, Level lc, float* __restrict__ m_fine,
-                                                  const float* __restrict__ m_coarse) {
+__device__ __forceinline__ float band_at(const BandSrc& b, size_t off) {
+    const float v = __ldg(b.a + off);
+    return b.b ? (v - __ldg(b.b + off)) * b.gain : v;
+}
+
+__global__ void __launch_bounds__(256) k_collapse(Level lf, Level lc, BandSrc fine, BandSrc coarse, float* __restrict__ out) {
     __shared__ __align__(16) float sD[DH][DP];
     const int plane = blockIdx.z;
     const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
-    const float* __restrict__ src = m_coarse + (size_t)plane * lc.plane;
+    const size_t cbase = (size_t)plane * lc.plane;
     for (int i = threadIdx.x; i < DH * DW; i += 256) {
         const int k = i / DW, j = i - k * DW;
         const int iy = upsrc(y0 / 2 - 1 + k, lc.h), ix = upsrc(x0 / 2 - 1 + j, lc.w);
-        sD[k][j] = __ldg(src + (size_t)iy * lc.pitch + ix);
+        sD[k][j] = band_at(coarse, cbase + (size_t)iy * lc.pitch + ix);
     }
     __syncthreads();
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
@@ -589,13 +596,17 @@ __global__ void __launch_bounds__(256) k_collapse(Level lf, Level lc, float* __r
         e[q][2] = p0.y + p1.x * 6.0f + p1.y;
         e[q][3] = (p1.x + p1.y) * 4.0f;
     }
-    float* __restrict__ mf = m_fine + (size_t)plane * lf.plane;
+    const size_t fbase = (size_t)plane * lf.plane;
 #pragma unroll
     for (int ry = 0; ry < 2; ++ry) {
         const int gy = y0 + 2 * ty + ry;
         if (gy >= lf.h) continue;
-        float4* p = reinterpret_cast<float4*>(mf + (size_t)gy * lf.pitch + gx);   // rows padded to 32 floats
-        float4 v = *p;
+        const size_t o = fbase + (size_t)gy * lf.pitch + gx;   // rows padded to 32 floats: a float4 at gx < w is in-bounds
+        float4 v = __ldg(reinterpret_cast<const float4*>(fine.a + o));
+        if (fine.b) {
+            const float4 u = __ldg(reinterpret_cast<const float4*>(fine.b + o));
+            v.x = (v.x - u.x) * fine.gain; v.y = (v.y - u.y) * fine.gain; v.z = (v.z - u.z) * fine.gain; v.w = (v.w - u.w) * fine.gain;
+        }
         if (ry == 0) {
             v.x = (e[0][0] + e[1][0] * 6.0f + e[2][0]) * kInv64 + v.x;
             v.y = (e[0][1] + e[1][1] * 6.0f + e[2][1]) * kInv64 + v.y;
@@ -607,7 +618,7 @@ __global__ void __launch_bounds__(256) k_collapse(Level lf, Level lc, float* __r
             v.z = ((e[1][2] + e[2][2]) * 4.0f) * kInv64 + v.z;
             v.w = ((e[1][3] + e[2][3]) * 4.0f) * kInv64 + v.w;
         }
-        *p = v;
+        *reinterpret_cast<float4*>(out + o) = v;
     }
 }
 
@@ -625,8 +636,8 @@ struct EgressArgs {
     uint8_t* out; size_t out_step, out_lane_stride;
     int w0, h0;
     const float4* gtab; LabInvCoeffs coeffs;
-    const float* m1; Level l1;      // band 1 (gain applied); null: no motion
-    const float* c2; Level l2;      // collapsed level 2; null: cur_1 = m_1
+    BandSrc m1; Level l1;           // band 1 = gain_1 * (hi_1 - lo_1) rebuilt from the state planes; a == null: no motion
+    BandSrc c2; Level l2;           // collapsed level 2 (or band 2 from state when it is the top band); a == null: cur_1 = m_1
     float chroma;
     float* fout;
 };
@@ -634,45 +645,70 @@ struct EgressArgs {
 template <int C>
 __global__ void __launch_bounds__(256) k_egress(const EgressArgs a) {
     __shared__ __align__(16) float sC2[C][E2H][E2P];
+    __shared__ __align__(16) float sT[C][E2H][DP];    // horizontal pyrUp pass of the level-2 window rows
     __shared__ __align__(16) float sD[C][DH][DP];
     const int lane = blockIdx.z;
     const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
     const int w1 = a.l1.w, h1 = a.l1.h;
-    if (a.m1) {
-        if (a.c2) {
-            // level-2 window (border rule of pyrUp pre-applied); one position per thread, channels inside
+    if (a.m1.a) {
+        // cur_1 = pyrUp(cur_2) + m_1 on the tile's level-1 window; m_1 = gain_1 * (hi_1 - lo_1) is rebuilt from the
+        // two state planes (a.m1.a, a.m1.b — always both, see launch_egress).  Position (k, j) of the window is
+        // level-1 pixel (y1, x1) = (upsrc(y0/2-1+k), upsrc(x0/2-1+j)).  pyrUp is evaluated separably: the
+        // horizontal pass of every level-2 window row at the 34 level-1 columns first (sT), then the vertical
+        // pass per position — same operation order as evaluating the 3x3 footprint per position, a fraction of
+        // the instructions.  Window index of level-2 pixel i is i - (x0/4 - 2); pyrUp's border rule is applied
+        // when the level-2 window is loaded (entries hold s[upsrc(i)]).
+        const bool has2 = a.c2.a != nullptr;
+        const int bx2 = x0 / 4 - 2, by2 = y0 / 4 - 2;
+        if (has2) {
+            const size_t base2 = (size_t)(lane * C) * a.l2.plane;
             for (int i = threadIdx.x; i < E2H * E2W; i += 256) {
                 const int k = i / E2W, j = i - k * E2W;
-                const int iy = upsrc(y0 / 4 - 2 + k, a.l2.h), ix = upsrc(x0 / 4 - 2 + j, a.l2.w);
-                const float* p2 = a.c2 + (size_t)(lane * C) * a.l2.plane + (size_t)iy * a.l2.pitch + ix;
+                const int o2 = upsrc(by2 + k, a.l2.h) * a.l2.pitch + upsrc(bx2 + j, a.l2.w);
 #pragma unroll
-                for (int ch = 0; ch < C; ++ch) sC2[ch][k][j] = __ldg(p2 + (size_t)ch * a.l2.plane);
+                for (int ch = 0; ch < C; ++ch) sC2[ch][k][j] = band_at(a.c2, base2 + (size_t)ch * a.l2.plane + o2);
+            }
+            __syncthreads();
+            for (int i = threadIdx.x; i < E2H * DW; i += 256) {
+                const int ky = i / DW, j = i - ky * DW;
+                const int x1 = upsrc(x0 / 2 - 1 + j, w1);
+                const int jx = (x1 >> 1) - bx2;
+                const bool odd = x1 & 1;
+#pragma unroll
+                for (int ch = 0; ch < C; ++ch) {
+                    const float sm = sC2[ch][ky][jx - 1], s0 = sC2[ch][ky][jx], sp = sC2[ch][ky][jx + 1];
+                    sT[ch][ky][j] = odd ? (s0 + sp) * 4.0f : (sm + s0 * 6.0f + sp);
+                }
             }
             __syncthreads();
         }
-        // level-1 window: position (k, j) <-> level-1 pixel upsrc(y0/2-1+k), upsrc(x0/2-1+j)
+        const float* __restrict__ ph[C];
+        const float* __restrict__ pl[C];
+#pragma unroll
+        for (int ch = 0; ch < C; ++ch) {
+            ph[ch] = a.m1.a + (size_t)(lane * C + ch) * a.l1.plane;
+            pl[ch] = a.m1.b + (size_t)(lane * C + ch) * a.l1.plane;
+        }
+        const float g1 = a.m1.gain;
         for (int i = threadIdx.x; i < DH * DW; i += 256) {
             const int k = i / DW, j = i - k * DW;
             const int y1 = upsrc(y0 / 2 - 1 + k, h1), x1 = upsrc(x0 / 2 - 1 + j, w1);
-            const float* p1 = a.m1 + (size_t)(lane * C) * a.l1.plane + (size_t)y1 * a.l1.pitch + x1;
-            // pyrUp of level 2 at (y1, x1): window index of level-2 pixel i is i - (x0/4 - 2); the border
-            // rule was applied when the window was loaded (entries hold s[upsrc(i)]).
-            const int jx = (x1 >> 1) - (x0 / 4 - 2), ky = (y1 >> 1) - (y0 / 4 - 2);
+            const int o1 = y1 * a.l1.pitch + x1;
+            float v[C];
 #pragma unroll
-            for (int ch = 0; ch < C; ++ch) {
-                float v = __ldg(p1 + (size_t)ch * a.l1.plane);
-                if (a.c2) {
-                    float r[3];
+            for (int ch = 0; ch < C; ++ch) v[ch] = (__ldg(ph[ch] + o1) - __ldg(pl[ch] + o1)) * g1;
+            if (has2) {
+                const int ky = (y1 >> 1) - by2;
+                const bool odd = y1 & 1;
 #pragma unroll
-                    for (int q = 0; q < 3; ++q) {
-                        const float* row = sC2[ch][ky - 1 + q];
-                        r[q] = (x1 & 1) ? (row[jx] + row[jx + 1]) * 4.0f : (row[jx - 1] + row[jx] * 6.0f + row[jx + 1]);
-                    }
-                    const float up = (y1 & 1) ? ((r[1] + r[2]) * 4.0f) * kInv64 : (r[0] + r[1] * 6.0f + r[2]) * kInv64;
-                    v = up + v;
+                for (int ch = 0; ch < C; ++ch) {
+                    const float r0 = sT[ch][ky - 1][j], r1 = sT[ch][ky][j], r2 = sT[ch][ky + 1][j];
+                    const float up = odd ? ((r1 + r2) * 4.0f) * kInv64 : (r0 + r1 * 6.0f + r2) * kInv64;
+                    v[ch] = up + v[ch];
                 }
-                sD[ch][k][j] = v;
             }
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch) sD[ch][k][j] = v[ch];
         }
         __syncthreads();
     }
@@ -680,7 +716,7 @@ __global__ void __launch_bounds__(256) k_egress(const EgressArgs a) {
     const int gx = x0 + 4 * tx;
     if (gx >= a.w0) return;
     float up[C][2][4];
-    if (a.m1) {
+    if (a.m1.a) {
 #pragma unroll
         for (int ch = 0; ch < C; ++ch) {
             float e[3][4];
@@ -717,7 +753,7 @@ __global__ void __launch_bounds__(256) k_egress(const EgressArgs a) {
                 float L = (float)vL[i] * (100.0f / 16384.0f);
                 float A = fmaf((float)vA[i], 1.0f / 64.0f, -128.0f);
                 float B = fmaf((float)vB[i], 1.0f / 64.0f, -128.0f);
-                if (a.m1) {
+                if (a.m1.a) {
                     // a,b motion planes *= chromAttenuation, then output = input + motion (MagnifyCore.hpp:140-148)
                     L = L + up[0][ry][i];
                     A = A + up[C > 1 ? 1 : 0][ry][i] * a.chroma;
@@ -735,7 +771,7 @@ __global__ void __launch_bounds__(256) k_egress(const EgressArgs a) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 float v = (gx + i < a.w0) ? u8_to_unit(__ldg(p + i)) : 0.0f;
-                if (a.m1) v = v + up[0][ry][i];
+                if (a.m1.a) v = v + up[0][ry][i];
                 of[i] = v;
                 o8[i] = unit_to_u8(v);
             }
@@ -847,15 +883,15 @@ cudaError_t launch_down(const LevelArgs& a, cudaStream_t s) {
     return cudaGetLastError();
 }
 
-cudaError_t launch_collapse(const Level& lf, const Level& lc, float* m_fine, const float* m_coarse, int planes,
+cudaError_t launch_collapse(const Level& lf, const Level& lc, const BandSrc& fine, const BandSrc& coarse, float* out, int planes,
                             cudaStream_t s) {
     dim3 grid(cdiv(lf.w, TW), cdiv(lf.h, TH), planes);
-    k_collapse<<<grid, 256, 0, s>>>(lf, lc, m_fine, m_coarse);
+    k_collapse<<<grid, 256, 0, s>>>(lf, lc, fine, coarse, out);
     return cudaGetLastError();
 }
 
 cudaError_t launch_egress(const FrameIO& io, const DeviceTables& tb, const int16_t* lab, int pitch16, size_t plane16,
-                          const float* m1, const Level& l1, const float* c2, const Level& l2, float chroma,
+                          const BandSrc& m1, const Level& l1, const BandSrc& c2, const Level& l2, float chroma,
                           float* fout, cudaStream_t s) {
     EgressArgs a;
     a.in = io.in; a.in_step = io.in_step; a.in_lane_stride = io.in_lane_stride;
@@ -863,6 +899,7 @@ cudaError_t launch_egress(const FrameIO& io, const DeviceTables& tb, const int16
     a.out = io.out; a.out_step = io.out_step; a.out_lane_stride = io.out_lane_stride;
     a.w0 = io.w; a.h0 = io.h;
     a.gtab = tb.inv_gamma; a.coeffs = tb.inv_coeffs;
+    if (m1.a && !m1.b) return cudaErrorInvalidValue;   // band 1 always comes from its two state plane sets
     a.m1 = m1; a.l1 = l1; a.c2 = c2; a.l2 = l2; a.chroma = chroma; a.fout = fout;
     dim3 grid(cdiv(io.w, TW), cdiv(io.h, TH), io.lanes);
     if (io.channels == 3) k_egress<3><<<grid, 256, 0, s>>>(a);

@@ -46,11 +46,13 @@ MC_HD uint8_t unit_to_u8(float x) {
     return (uint8_t)(int)v;
 }
 
-// same for x known to lie in [0, 1+eps] (or NaN): round-half-even, NaN -> 0, min with 255
+// same on the device in one conversion instruction: cvt.rni.u8.f32 rounds half to even and clamps to [0, 255]
+// (float -> integer conversions saturate; NaN -> 0), which is exactly cvRound + saturate_cast<uchar>.
 MC_HD uint8_t unit01_to_u8(float x) {
-#if defined(__CUDA_ARCH__)
-    const int v = __float2int_rn(fmaf(x, 255.0f, 0.003921568859368563f));
-    return (uint8_t)min(max(v, 0), 255);
+#if defined(__CUDA_ARCH__) && !defined(MC_CUDA_EMU)
+    unsigned r;
+    asm("cvt.rni.u8.f32 %0, %1;" : "=r"(r) : "f"(fmaf(x, 255.0f, 0.003921568859368563f)));
+    return (uint8_t)r;
 #else
     return unit_to_u8(x);
 #endif

@@ -56,7 +56,8 @@ mc_status MotionMode::allocate(const ModeCtx& ctx, const FrameIO& io, int nlevel
             MCK(arena.alloc(&hi[(size_t)l], n));
             MCK(arena.alloc(&lo[(size_t)l], n));
         }
-        if (live) MCK(arena.alloc(&M[(size_t)l], n));
+        // collapsed levels cur_2 .. cur_{levels-2}; the bands themselves are rebuilt from hi/lo by their consumers
+        if (live && l >= 2 && l <= levels - 2) MCK(arena.alloc(&M[(size_t)l], n));
     }
     // TMA descriptors for the f32 inputs of the fused level kernels
     tmaps.assign((size_t)levels + 1, TensorMapStorage{});
@@ -114,7 +115,7 @@ mc_status MotionMode::process(const ModeCtx& ctx, const FrameIO& io, const mc_pa
         a.lf = lv[(size_t)l]; a.lc = lv[(size_t)l + 1];
         a.g_next = G[(size_t)l + 1];
         a.hi = hi[(size_t)l]; a.lo = lo[(size_t)l];
-        a.m = first ? nullptr : M[(size_t)l];
+        a.m = nullptr;   // gain * (hi - lo) is rebuilt by the collapse / egress kernels from the state planes
         a.planes = planes;
         a.first = first ? 1 : 0;
         a.band = (l >= 1 || faithful) ? 1 : 0;
@@ -129,15 +130,16 @@ mc_status MotionMode::process(const ModeCtx& ctx, const FrameIO& io, const mc_pa
         LAUNCH("copy", levels, launch_copy_planes(hi[(size_t)levels], G[(size_t)levels], n, ctx.stream));
         LAUNCH("copy", levels, launch_copy_planes(lo[(size_t)levels], G[(size_t)levels], n, ctx.stream));
     }
-    const float* m1 = nullptr;
-    const float* c2 = nullptr;
+    BandSrc m1, c2;
     if (!first && levels >= 2) {
-        // synthesis: residual and finest band are zero (MagnifyCore.hpp:130-131), so the collapse
-        // starts from band levels-1; levels 1 and 0 are folded into egress.
+        // synthesis: residual and finest band are zero (MagnifyCore.hpp:130-131), so the collapse starts from
+        // band levels-1 (cur_{levels-1} = 0 + m_{levels-1}); levels 1 and 0 are folded into egress.
+        auto band = [&](int l) { return BandSrc{hi[(size_t)l], lo[(size_t)l], gains[(size_t)l]}; };
+        auto cur = [&](int l) { return l == levels - 1 ? band(l) : BandSrc{M[(size_t)l], nullptr, 1.0f}; };
         for (int l = levels - 2; l >= 2; --l)
-            LAUNCH("collapse", l, launch_collapse(lv[(size_t)l], lv[(size_t)l + 1], M[(size_t)l], M[(size_t)l + 1], planes, ctx.stream));
-        m1 = M[1];
-        if (levels >= 3) c2 = M[2];
+            LAUNCH("collapse", l, launch_collapse(lv[(size_t)l], lv[(size_t)l + 1], band(l), cur(l + 1), M[(size_t)l], planes, ctx.stream));
+        m1 = band(1);
+        if (levels >= 3) c2 = cur(2);
     }
     const Level& l1 = lv[levels >= 1 ? 1 : 0];
     const Level& l2 = lv[levels >= 2 ? 2 : 0];

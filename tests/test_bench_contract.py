@@ -35,3 +35,23 @@ def test_product_arm_needs_a_gpu():
                        capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
     assert not [l for l in r.stdout.splitlines() if l.startswith("{")]
+
+
+def test_kernel_table_accounting():
+    """bench.kernel_table: interface / algorithmic byte models per kernel (no GPU needed) — the level kernel no
+    longer stores its band (16 B of state + 4 B in + 1 B out per pixel), and stale ncu captures are dropped."""
+    sys.path.insert(0, ROOT)
+    import bench
+    px = bench.level_pixels(1920, 1080, 6)
+    prof = {("ingest_lab", 0): (20, 10.3), ("egress", 0): (20, 8.0), ("level", 1): (20, 4.0), ("level", 2): (20, 1.3),
+            ("collapse", 2): (20, 0.6), ("collapse", 4): (20, 0.2)}
+    table, traffic = bench.kernel_table(prof, 32)
+    by = {t["kernel"]: t for t in table}
+    assert [t["kernel"] for t in table][0] == "ingest_lab[0]"                       # sorted by time share
+    assert by["level[1]"]["interface_bytes"] == 32 * 3 * (16 * px[1] + 4 * px[1] + 4 * px[2])
+    assert by["collapse[2]"]["interface_bytes"] == 32 * 3 * (12 * px[2] + 4 * px[3])
+    assert by["collapse[4]"]["interface_bytes"] == 32 * 3 * (12 * px[4] + 8 * px[5])  # top band comes from state planes
+    assert by["egress[0]"]["interface_bytes"] == 32 * 3 * (3 * px[0] + 8 * px[1] + 4 * px[2])
+    assert abs(by["level[1]"]["algorithmic_GBps"] - 16 * 3 * px[1] * 32 / 200e-6 / 1e9) < 1e-6
+    assert abs(sum(t["share"] for t in table) - 1.0) < 1e-9
+    assert "level[1]" not in traffic and "egress[0]" not in traffic                 # captures of the older interface
