@@ -191,7 +191,7 @@ def run_reference(args, rank, world):
     })
 
 
-def kernel_table(prof, lanes):
+def kernel_table(prof, lanes, band_from_state=False):
     """prof: {(kernel name, level): (launches, total ms)} from mc_profile_read -> (per-kernel table sorted by time share,
     {kernel: ncu DRAM bytes per launch scaled to `lanes`} from profiles/traffic.json for captures that still apply)."""
     px = level_pixels(W, H, LEVELS)
@@ -201,7 +201,8 @@ def kernel_table(prof, lanes):
         # alg = this kernel's share of A_min; io = bytes its interface forces through HBM
         if name == "level" and lvl >= 1:
             alg = 16 * CH * px[lvl] * lanes                       # two f32 state planes, read + write
-            io = alg + 4 * CH * (px[lvl] + px[lvl + 1]) * lanes    # + G_l read, G_{l+1} write (the band is not stored)
+            # + G_l read, G_{l+1} write, and the band M_l write unless the synthesis rebuilds it from hi/lo
+            io = alg + 4 * CH * (px[lvl] * (1 if band_from_state else 2) + px[lvl + 1]) * lanes
         elif name in ("level", "down"):                           # level 0: Lab16 -> pyrDown -> G1
             alg = 0
             io = (2 * CH * px[0] + 4 * CH * px[1]) * lanes
@@ -213,11 +214,16 @@ def kernel_table(prof, lanes):
             io = alg + 2 * CH * px[0] * lanes                     # + Lab16 write
         elif name == "egress":
             alg = CH * px[0] * lanes                              # u8 frame write
-            # + Lab16 read, hi_1/lo_1 read (band 1 rebuilt from state), cur_2 read
-            io = alg + (2 * CH * px[0] + 8 * CH * px[1] + (8 if LEVELS == 3 else 4) * CH * px[2]) * lanes
-        else:                                                     # collapse: hi_l/lo_l read, cur_l write, cur_{l+1} read
+            if band_from_state:   # + Lab16 read, hi_1/lo_1 read (band 1 rebuilt from state), cur_2 read
+                io = alg + (2 * CH * px[0] + 8 * CH * px[1] + (8 if LEVELS == 3 else 4) * CH * px[2]) * lanes
+            else:                 # + Lab16 read, M_1 read, cur_2 read
+                io = alg + (2 * CH * px[0] + 4 * CH * px[1] + 4 * CH * px[2]) * lanes
+        else:                                                     # collapse
             alg = 0
-            io = (12 * px[lvl] + (8 if lvl + 1 == LEVELS - 1 else 4) * px[lvl + 1]) * CH * lanes
+            if band_from_state:   # hi_l/lo_l read, cur_l write, cur_{l+1} read (from state when it is the top band)
+                io = (12 * px[lvl] + (8 if lvl + 1 == LEVELS - 1 else 4) * px[lvl + 1]) * CH * lanes
+            else:                 # M_l read + write, M_{l+1} read
+                io = (8 * px[lvl] + 4 * px[lvl + 1]) * CH * lanes
         us = tms / n * 1e3
         table.append({"kernel": f"{name}[{lvl}]", "us_per_launch": us, "share": tms / total_ms,
                       "algorithmic_GBps": alg / (us * 1e-6) / 1e9, "interface_GBps": io / (us * 1e-6) / 1e9,

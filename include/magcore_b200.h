@@ -156,7 +156,10 @@ void* mc_stream(mc_handle* h);
  *   "keep_float_output" (default 0): keep the pre-quantisation float image (tests)
  *   "profile_kernels" (default 0): see mc_profile_read
  *   "use_tma" (default 1): stage the fused level kernel's tiles with TMA (cp.async.bulk.tensor); 0 selects
- *        the 128-bit LDG staging path (same results; kept for A/B measurements) */
+ *        the 128-bit LDG staging path (same results; kept for A/B measurements)
+ *   "band_from_state" (default 0): Laplace synthesis rebuilds each amplified band gain*(hi-lo) from the two
+ *        state planes instead of reading a band plane stored by the level kernel (same results; takes 4 B/px off
+ *        the level kernel's interface and adds them to the collapse / egress kernels; kept for A/B measurements) */
 mc_status mc_set_option(mc_handle* h, const char* key, int value);
 
 /* Test-only access to temporal state planes as dense f32 [lanes][channels][rows][cols].

@@ -101,7 +101,7 @@ struct BandSrc {
     float gain = 1.0f;
 };
 
-// out_l = pyrUp(coarse) + fine (SpatialFilter.cpp:52-61); `out` may not alias the inputs
+// out_l = pyrUp(coarse) + fine (SpatialFilter.cpp:52-61); `out` may be the stored fine plane itself (in place)
 cudaError_t launch_collapse(const Level& lf, const Level& lc, const BandSrc& fine, const BandSrc& coarse, float* out, int planes,
                             cudaStream_t s);
 

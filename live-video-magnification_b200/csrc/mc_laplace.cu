@@ -562,17 +562,17 @@ __global__ void __launch_bounds__(32 * IG_WARPS) k_ingest_lab(const IngestArgs a
 
 // ------------------------------------------------------------------------------------------------
 // collapse: cur_l = pyrUp(cur_{l+1}) + m_l.  The band-passed, amplified band m_l = gain_l * (hi_l - lo_l)
-// (TemporalFilter.cpp:21, MagnifyCore.hpp:127-134) is not stored by the level kernel: it is rebuilt here
-// from the two state planes the level kernel has just written (same f32 subtract and multiply), which
-// takes 4 B/px off the HBM-bound level kernel's interface.  Tile 64 x 32, thread block 4 x 2 (same
-// register pyrUp as the level kernel), 128-bit accesses.
+// (TemporalFilter.cpp:21, MagnifyCore.hpp:127-134) is either the plane the level kernel stored (then `out` may be
+// that same plane: every thread reads its pixels before it writes them) or, with option band_from_state, rebuilt
+// from the two state planes the level kernel has just written (same f32 subtract and multiply).  Tile 64 x 32,
+// thread block 4 x 2 (same register pyrUp as the level kernel), 128-bit accesses.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float band_at(const BandSrc& b, size_t off) {
     const float v = __ldg(b.a + off);
     return b.b ? (v - __ldg(b.b + off)) * b.gain : v;
 }
 
-__global__ void __launch_bounds__(256) k_collapse(Level lf, Level lc, BandSrc fine, BandSrc coarse, float* __restrict__ out) {
+__global__ void __launch_bounds__(256) k_collapse(Level lf, Level lc, BandSrc fine, BandSrc coarse, float* out) {
     __shared__ __align__(16) float sD[DH][DP];
     const int plane = blockIdx.z;
     const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
@@ -602,7 +602,7 @@ __global__ void __launch_bounds__(256) k_collapse(Level lf, Level lc, BandSrc fi
         const int gy = y0 + 2 * ty + ry;
         if (gy >= lf.h) continue;
         const size_t o = fbase + (size_t)gy * lf.pitch + gx;   // rows padded to 32 floats: a float4 at gx < w is in-bounds
-        float4 v = __ldg(reinterpret_cast<const float4*>(fine.a + o));
+        float4 v = *reinterpret_cast<const float4*>(fine.a + o);   // plain load: `out` may be this very plane
         if (fine.b) {
             const float4 u = __ldg(reinterpret_cast<const float4*>(fine.b + o));
             v.x = (v.x - u.x) * fine.gain; v.y = (v.y - u.y) * fine.gain; v.z = (v.z - u.z) * fine.gain; v.w = (v.w - u.w) * fine.gain;
@@ -651,8 +651,8 @@ __global__ void __launch_bounds__(256) k_egress(const EgressArgs a) {
     const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
     const int w1 = a.l1.w, h1 = a.l1.h;
     if (a.m1.a) {
-        // cur_1 = pyrUp(cur_2) + m_1 on the tile's level-1 window; m_1 = gain_1 * (hi_1 - lo_1) is rebuilt from the
-        // two state planes (a.m1.a, a.m1.b — always both, see launch_egress).  Position (k, j) of the window is
+        // cur_1 = pyrUp(cur_2) + m_1 on the tile's level-1 window; m_1 is the stored band plane, or gain_1 * (hi_1 - lo_1)
+        // rebuilt from the two state planes (option band_from_state).  Position (k, j) of the window is
         // level-1 pixel (y1, x1) = (upsrc(y0/2-1+k), upsrc(x0/2-1+j)).  pyrUp is evaluated separably: the
         // horizontal pass of every level-2 window row at the 34 level-1 columns first (sT), then the vertical
         // pass per position — same operation order as evaluating the 3x3 footprint per position, a fraction of
@@ -687,16 +687,20 @@ __global__ void __launch_bounds__(256) k_egress(const EgressArgs a) {
 #pragma unroll
         for (int ch = 0; ch < C; ++ch) {
             ph[ch] = a.m1.a + (size_t)(lane * C + ch) * a.l1.plane;
-            pl[ch] = a.m1.b + (size_t)(lane * C + ch) * a.l1.plane;
+            pl[ch] = a.m1.b ? a.m1.b + (size_t)(lane * C + ch) * a.l1.plane : nullptr;
         }
         const float g1 = a.m1.gain;
+        const bool from_state = a.m1.b != nullptr;
         for (int i = threadIdx.x; i < DH * DW; i += 256) {
             const int k = i / DW, j = i - k * DW;
             const int y1 = upsrc(y0 / 2 - 1 + k, h1), x1 = upsrc(x0 / 2 - 1 + j, w1);
             const int o1 = y1 * a.l1.pitch + x1;
             float v[C];
 #pragma unroll
-            for (int ch = 0; ch < C; ++ch) v[ch] = (__ldg(ph[ch] + o1) - __ldg(pl[ch] + o1)) * g1;
+            for (int ch = 0; ch < C; ++ch) {
+                v[ch] = __ldg(ph[ch] + o1);
+                if (from_state) v[ch] = (v[ch] - __ldg(pl[ch] + o1)) * g1;
+            }
             if (has2) {
                 const int ky = (y1 >> 1) - by2;
                 const bool odd = y1 & 1;
@@ -899,7 +903,6 @@ cudaError_t launch_egress(const FrameIO& io, const DeviceTables& tb, const int16
     a.out = io.out; a.out_step = io.out_step; a.out_lane_stride = io.out_lane_stride;
     a.w0 = io.w; a.h0 = io.h;
     a.gtab = tb.inv_gamma; a.coeffs = tb.inv_coeffs;
-    if (m1.a && !m1.b) return cudaErrorInvalidValue;   // band 1 always comes from its two state plane sets
     a.m1 = m1; a.l1 = l1; a.c2 = c2; a.l2 = l2; a.chroma = chroma; a.fout = fout;
     dim3 grid(cdiv(io.w, TW), cdiv(io.h, TH), io.lanes);
     if (io.channels == 3) k_egress<3><<<grid, 256, 0, s>>>(a);

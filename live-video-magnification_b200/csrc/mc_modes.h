@@ -35,6 +35,8 @@ struct ModeCtx {
     float* float_out;  // optional [lanes][h][w][C] pre-quantisation tap
     Profiler* prof;    // optional
     bool use_tma;      // stage level-kernel tiles with cp.async.bulk.tensor (option "use_tma", default on)
+    bool band_from_state;   // synthesis rebuilds gain*(hi-lo) from the state planes instead of reading a stored band
+                            // (option "band_from_state", default off: measured no faster on B200)
 };
 
 // Launch bookkeeping shared by the mode drivers: counts the launch, optionally brackets it with events.
@@ -78,6 +80,7 @@ struct MotionMode {
     bool allocated = false;
     int levels = 0, channels = 0, w = 0, h = 0;
     bool faithful = false;
+    bool from_state = false;   // ModeCtx::band_from_state at allocation time
     std::vector<Level> lv;              // 0..levels
     std::vector<float*> G, hi, lo, M;   // per level (null where not kept)
     int16_t* lab16 = nullptr;           // Lab planes of the current frame (C == 3)

@@ -35,6 +35,7 @@ mc_status MotionMode::allocate(const ModeCtx& ctx, const FrameIO& io, int nlevel
     reset();
     levels = nlevels; channels = io.channels; w = io.w; h = io.h;
     faithful = ctx.faithful0;
+    from_state = ctx.band_from_state;
     const size_t planes = (size_t)lanes * channels;
     lv.resize((size_t)levels + 1);
     int cw = w, ch = h;
@@ -56,8 +57,9 @@ mc_status MotionMode::allocate(const ModeCtx& ctx, const FrameIO& io, int nlevel
             MCK(arena.alloc(&hi[(size_t)l], n));
             MCK(arena.alloc(&lo[(size_t)l], n));
         }
-        // collapsed levels cur_2 .. cur_{levels-2}; the bands themselves are rebuilt from hi/lo by their consumers
-        if (live && l >= 2 && l <= levels - 2) MCK(arena.alloc(&M[(size_t)l], n));
+        // M_l: the amplified band of level l, overwritten by the collapsed cur_l.  With band_from_state the bands are
+        // rebuilt from hi/lo by their consumers and only cur_2 .. cur_{levels-2} are materialised.
+        if (live && (!from_state || (l >= 2 && l <= levels - 2))) MCK(arena.alloc(&M[(size_t)l], n));
     }
     // TMA descriptors for the f32 inputs of the fused level kernels
     tmaps.assign((size_t)levels + 1, TensorMapStorage{});
@@ -76,7 +78,7 @@ mc_status MotionMode::allocate(const ModeCtx& ctx, const FrameIO& io, int nlevel
 }
 
 mc_status MotionMode::process(const ModeCtx& ctx, const FrameIO& io, const mc_params& p, int nlevels, int* produced) {
-    if (!allocated || faithful != ctx.faithful0) {
+    if (!allocated || faithful != ctx.faithful0 || from_state != ctx.band_from_state) {
         mc_status st = allocate(ctx, io, nlevels);
         if (st != MC_OK) return st;
     }
@@ -115,7 +117,7 @@ mc_status MotionMode::process(const ModeCtx& ctx, const FrameIO& io, const mc_pa
         a.lf = lv[(size_t)l]; a.lc = lv[(size_t)l + 1];
         a.g_next = G[(size_t)l + 1];
         a.hi = hi[(size_t)l]; a.lo = lo[(size_t)l];
-        a.m = nullptr;   // gain * (hi - lo) is rebuilt by the collapse / egress kernels from the state planes
+        a.m = (first || from_state) ? nullptr : M[(size_t)l];
         a.planes = planes;
         a.first = first ? 1 : 0;
         a.band = (l >= 1 || faithful) ? 1 : 0;
@@ -134,7 +136,9 @@ mc_status MotionMode::process(const ModeCtx& ctx, const FrameIO& io, const mc_pa
     if (!first && levels >= 2) {
         // synthesis: residual and finest band are zero (MagnifyCore.hpp:130-131), so the collapse starts from
         // band levels-1 (cur_{levels-1} = 0 + m_{levels-1}); levels 1 and 0 are folded into egress.
-        auto band = [&](int l) { return BandSrc{hi[(size_t)l], lo[(size_t)l], gains[(size_t)l]}; };
+        auto band = [&](int l) {
+            return from_state ? BandSrc{hi[(size_t)l], lo[(size_t)l], gains[(size_t)l]} : BandSrc{M[(size_t)l], nullptr, 1.0f};
+        };
         auto cur = [&](int l) { return l == levels - 1 ? band(l) : BandSrc{M[(size_t)l], nullptr, 1.0f}; };
         for (int l = levels - 2; l >= 2; --l)
             LAUNCH("collapse", l, launch_collapse(lv[(size_t)l], lv[(size_t)l + 1], band(l), cur(l + 1), M[(size_t)l], planes, ctx.stream));

@@ -38,8 +38,9 @@ def test_product_arm_needs_a_gpu():
 
 
 def test_kernel_table_accounting():
-    """bench.kernel_table: interface / algorithmic byte models per kernel (no GPU needed) — the level kernel no
-    longer stores its band (16 B of state + 4 B in + 1 B out per pixel), and stale ncu captures are dropped."""
+    """bench.kernel_table: interface / algorithmic byte models per kernel (no GPU needed), for the default data flow
+    (level kernels store their band) and for option band_from_state; ncu captures are only quoted for kernels whose
+    interface still matches the capture."""
     sys.path.insert(0, ROOT)
     import bench
     px = bench.level_pixels(1920, 1080, 6)
@@ -48,10 +49,16 @@ def test_kernel_table_accounting():
     table, traffic = bench.kernel_table(prof, 32)
     by = {t["kernel"]: t for t in table}
     assert [t["kernel"] for t in table][0] == "ingest_lab[0]"                       # sorted by time share
-    assert by["level[1]"]["interface_bytes"] == 32 * 3 * (16 * px[1] + 4 * px[1] + 4 * px[2])
-    assert by["collapse[2]"]["interface_bytes"] == 32 * 3 * (12 * px[2] + 4 * px[3])
-    assert by["collapse[4]"]["interface_bytes"] == 32 * 3 * (12 * px[4] + 8 * px[5])  # top band comes from state planes
-    assert by["egress[0]"]["interface_bytes"] == 32 * 3 * (3 * px[0] + 8 * px[1] + 4 * px[2])
+    assert by["level[1]"]["interface_bytes"] == 32 * 3 * (16 * px[1] + 8 * px[1] + 4 * px[2])
+    assert by["collapse[2]"]["interface_bytes"] == 32 * 3 * (8 * px[2] + 4 * px[3])
+    assert by["egress[0]"]["interface_bytes"] == 32 * 3 * (3 * px[0] + 4 * px[1] + 4 * px[2])
     assert abs(by["level[1]"]["algorithmic_GBps"] - 16 * 3 * px[1] * 32 / 200e-6 / 1e9) < 1e-6
     assert abs(sum(t["share"] for t in table) - 1.0) < 1e-9
-    assert "level[1]" not in traffic and "egress[0]" not in traffic                 # captures of the older interface
+    assert {"ingest_lab[0]", "egress[0]", "level[1]"} <= set(traffic)               # captures match this data flow
+    table2, traffic2 = bench.kernel_table(prof, 32, band_from_state=True)
+    by2 = {t["kernel"]: t for t in table2}
+    assert by2["level[1]"]["interface_bytes"] == 32 * 3 * (16 * px[1] + 4 * px[1] + 4 * px[2])
+    assert by2["collapse[2]"]["interface_bytes"] == 32 * 3 * (12 * px[2] + 4 * px[3])
+    assert by2["collapse[4]"]["interface_bytes"] == 32 * 3 * (12 * px[4] + 8 * px[5])  # top band comes from state planes
+    assert by2["egress[0]"]["interface_bytes"] == 32 * 3 * (3 * px[0] + 8 * px[1] + 4 * px[2])
+    assert "level[1]" not in traffic2 and "egress[0]" not in traffic2                # stale for that data flow

@@ -272,3 +272,16 @@ def test_empty_image_and_mode_none_free_state():
     assert proc.state_dims("lowpassHi", 1)[0] == 0
     produced, _ = proc.process_image(synth_frame(1, 64, 48, 3), cfg)              # starts again as a first frame
     assert produced
+
+
+def test_band_from_state_option_equals_stored_band():
+    """Option band_from_state (synthesis rebuilds gain*(hi-lo) from the state planes) must not change a single bit."""
+    for (w, h, c, levels) in ((322, 241, 3, 5), (131, 75, 1, 3), (200, 120, 3, 2), (640, 360, 3, 6)):
+        cfg, _ = make_cfgs(O.MODE_LAPLACE, 20, 50.0, 0.4, 3.0, 30, levels)
+        a, b = L.MagnificationProcessor(0), L.MagnificationProcessor(0)
+        b.set_option("band_from_state", 1)
+        for t in range(5):
+            f = synth_frame(t, w, h, c)
+            _, oa = a.process_image(f, cfg)
+            _, ob = b.process_image(f, cfg)
+            assert np.array_equal(oa, ob), (w, h, t)

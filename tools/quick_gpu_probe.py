@@ -1,0 +1,60 @@
+#!/usr/bin/env python
+"""Torch-free GPU probe (seconds, for tight gpurun budgets): parity of the Laplace path against the checker on a
+small and a 1080p clip, then the per-kernel device-time table (profile_kernels) of the 1080p bench workload through
+the blocking host API.  Prints one JSON line."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    t00 = time.time()
+    import lvm_b200 as L
+    from lvm_b200.synth import synth_frame
+    from oracle import livim_oracle as O, livim_ref
+    from common import make_cfgs
+    out = {}
+    R = livim_ref.load()
+    for (w, h, levels, n) in ((320, 240, 4, 6), (1920, 1080, 6, 3)):
+        cfg, ocfg = make_cfgs(O.MODE_LAPLACE, 20, 50.0, 0.4, 3.0, 30, levels)
+        proc = L.MagnificationProcessor(0)
+        ref = R.Processor() if R is not None else O.MagnificationProcessor()
+        rcfg = livim_ref.to_ref_config(R, ocfg) if R is not None else ocfg
+        worst, ndiff = 0, 0
+        for t in range(n):
+            f = synth_frame(t, w, h, 3)
+            _, o = proc.process_image(f, cfg)
+            _, ro = ref.process(f, rcfg)
+            d = np.abs(o.astype(np.int32) - ro.astype(np.int32))
+            worst, ndiff = max(worst, int(d.max())), ndiff + int((d > 0).sum())
+        out[f"parity_{w}x{h}"] = {"max_u8_diff": worst, "differing": ndiff, "checker": "reference" if R is not None else "oracle"}
+        proc.close()
+    lanes = int(os.environ.get("PROBE_LANES", "8"))
+    cfg, _ = make_cfgs(O.MODE_LAPLACE, 20, 50.0, 0.4, 3.0, 0, 6)
+    base = [synth_frame(t, 1920, 1080, 3) for t in range(2)]
+    clip = [np.stack([np.roll(base[t], (11 * k, 37 * k), axis=(0, 1)) for k in range(lanes)]) for t in range(2)]
+    proc = L.MagnificationProcessor(0, lanes=lanes)
+    for i in range(3):
+        proc.process_image(clip[i % 2], cfg)
+    proc.set_option("profile_kernels", 1)
+    for i in range(8):
+        proc.process_image(clip[i % 2], cfg)
+    prof = proc.profile_read()
+    table = sorted(((f"{k}[{lvl}]", tms / n * 1e3) for (k, lvl), (n, tms) in prof.items()), key=lambda r: -r[1])
+    out["lanes"] = lanes
+    out["kernels_us"] = {k: round(us, 1) for k, us in table}
+    out["step_us"] = round(sum(us for _, us in table), 1)
+    out["fps_device_kernels_only"] = round(lanes / (out["step_us"] * 1e-6), 1)
+    out["seconds"] = round(time.time() - t00, 1)
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
