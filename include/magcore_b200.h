@@ -157,6 +157,8 @@ void* mc_stream(mc_handle* h);
  *   "profile_kernels" (default 0): see mc_profile_read
  *   "use_tma" (default 1): stage the fused level kernel's tiles with TMA (cp.async.bulk.tensor); 0 selects
  *        the 128-bit LDG staging path (same results; kept for A/B measurements)
+ *   "analysis_only" (default 0): Laplace only — frames after the first update the temporal state but skip
+ *        synthesis and egress and report *produced = 0; the cheap first pass of temporal sharding
  *   "band_from_state" (default 0): Laplace synthesis rebuilds each amplified band gain*(hi-lo) from the two
  *        state planes instead of reading a band plane stored by the level kernel (same results; takes 4 B/px off
  *        the level kernel's interface and adds them to the collapse / egress kernels; kept for A/B measurements) */

@@ -37,6 +37,8 @@ struct ModeCtx {
     bool use_tma;      // stage level-kernel tiles with cp.async.bulk.tensor (option "use_tma", default on)
     bool band_from_state;   // synthesis rebuilds gain*(hi-lo) from the state planes instead of reading a stored band
                             // (option "band_from_state", default off: measured no faster on B200)
+    bool analysis_only;     // Laplace: update the temporal state but skip synthesis + egress (*produced = 0); used by the
+                            // state-carry pass of temporal sharding (lvm_b200.shard.magnify_segment)
 };
 
 // Launch bookkeeping shared by the mode drivers: counts the launch, optionally brackets it with events.

@@ -132,6 +132,10 @@ mc_status MotionMode::process(const ModeCtx& ctx, const FrameIO& io, const mc_pa
         LAUNCH("copy", levels, launch_copy_planes(hi[(size_t)levels], G[(size_t)levels], n, ctx.stream));
         LAUNCH("copy", levels, launch_copy_planes(lo[(size_t)levels], G[(size_t)levels], n, ctx.stream));
     }
+    if (ctx.analysis_only && !first) {   // state-carry pass: the temporal state is up to date, no frame is produced
+        *produced = 0;
+        return MC_OK;
+    }
     BandSrc m1, c2;
     if (!first && levels >= 2) {
         // synthesis: residual and finest band are zero (MagnifyCore.hpp:130-131), so the collapse starts from
