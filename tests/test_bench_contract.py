@@ -62,3 +62,58 @@ def test_kernel_table_accounting():
     assert by2["collapse[4]"]["interface_bytes"] == 32 * 3 * (12 * px[4] + 8 * px[5])  # top band comes from state planes
     assert by2["egress[0]"]["interface_bytes"] == 32 * 3 * (3 * px[0] + 8 * px[1] + 4 * px[2])
     assert "level[1]" not in traffic2 and "egress[0]" not in traffic2                # stale for that data flow
+
+
+@pytest.mark.emu
+def test_product_arm_dry_run_on_emulation(monkeypatch):
+    """bench.run_ours end to end (device-resident loop, pipelined e2e loop, per-kernel table, CPU baseline, JSON line)
+    with the kernels on the CUDA-on-CPU emulation and a stand-in for the handful of torch.cuda calls it makes, at a
+    tiny frame size.  Guards the bench's own logic in the GPU-less container; the numbers mean nothing."""
+    import time
+    import types
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: the real bench runs")
+    sys.path.insert(0, ROOT)
+    import bench
+    import conftest
+    from lvm_b200 import capi
+    saved = (capi.LIB_PATH, capi._lib)
+    conftest.use_emulated_library()
+
+    class FakeEvent:
+        def __init__(self, enable_timing=False):
+            self.t = 0.0
+
+        def record(self, stream=None):
+            self.t = time.perf_counter()
+
+        def elapsed_time(self, other):
+            return (other.t - self.t) * 1e3
+
+    real_empty = torch.empty
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    monkeypatch.setattr(torch.cuda, "set_device", lambda d: None)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a: None)
+    monkeypatch.setattr(torch.cuda, "ExternalStream", lambda ptr, device=None: types.SimpleNamespace(ptr=ptr))
+    monkeypatch.setattr(torch.cuda, "Event", FakeEvent)
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: self)
+    monkeypatch.setattr(torch, "empty", lambda *a, **k: real_empty(*a, **{kk: v for kk, v in k.items() if kk != "device"}))
+    monkeypatch.setattr(bench, "W", 192)
+    monkeypatch.setattr(bench, "H", 108)
+    monkeypatch.setattr(bench, "LEVELS", 4)
+    monkeypatch.setitem(bench.UI, "levels", 4)
+    try:
+        args = types.SimpleNamespace(gpus=1, steps=3, warmup=3, lanes=2, clip_frames=2, cpu_frames=2, no_cpu_baseline=False,
+                                     ref_frames_per_step=1)
+        d = json.loads(bench.run_ours(args, 0, 1, 0))
+    finally:
+        capi.LIB_PATH, capi._lib = saved
+    assert d["metric"] == "1080p frames/sec (Laplace, 6-level)" and d["unit"] == "frames/s" and d["n_gpus"] == 1
+    assert d["value"] > 0 and d["e2e"]["value"] > 0 and d["steps"] == 3 and d["warmup"] == 3
+    assert d["e2e"]["h2d_bytes_per_step"] == d["e2e"]["d2h_bytes_per_step"] == 2 * 192 * 108 * 3
+    assert d["gpu_launches"] == 3 * 6                      # 4 levels: ingest, level 1-3, collapse 2, egress per step
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and 0 < r["frac"] and r["fused_level_kernel"]["kernel"] == "level[1]"
+    assert {k["kernel"] for k in r["kernels"]} >= {"ingest_lab[0]", "egress[0]", "level[1]", "level[2]", "level[3]", "collapse[2]"}
+    assert d["cpu_baseline"]["value"] > 0 and d["cpu_baseline"]["kind"] in ("reference", "port")
