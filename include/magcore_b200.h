@@ -157,6 +157,9 @@ void* mc_stream(mc_handle* h);
  *   "profile_kernels" (default 0): see mc_profile_read
  *   "use_tma" (default 1): stage the fused level kernel's tiles with TMA (cp.async.bulk.tensor); 0 selects
  *        the 128-bit LDG staging path (same results; kept for A/B measurements)
+ *   "prefetch_state" (default 0; needs use_tma): the fused level kernel requests the tile's two state planes as TMA
+ *        bulk copies at kernel entry, together with its input window, instead of loading them in its last phase
+ *        (same results; for A/B measurements — the kernel is latency-bound)
  *   "analysis_only" (default 0): Laplace only — frames after the first update the temporal state but skip
  *        synthesis and egress and report *produced = 0; the cheap first pass of temporal sharding
  *   "band_from_state" (default 0): Laplace synthesis rebuilds each amplified band gain*(hi-lo) from the two

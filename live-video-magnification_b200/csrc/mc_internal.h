@@ -82,10 +82,11 @@ struct LevelArgs {
     double c_hi = 0, one_minus_c_hi = 0, c_lo = 0, one_minus_c_lo = 0;
     float gain = 0;
     const void* tmap = nullptr;   // CUtensorMap of the f32 input planes (TMA-staged tile) or null
+    const void* tmap_hi = nullptr, *tmap_lo = nullptr;   // CUtensorMaps of the state planes: prefetch their tiles too
 };
 // 128-byte opaque CUtensorMap storage + encoder for the level kernel's (72 x 39 x 1) box
 struct alignas(64) TensorMapStorage { unsigned char bytes[128]; };
-bool make_level_tensor_map(void* out_map, const float* base, const Level& l, int planes);
+bool make_level_tensor_map(void* out_map, const float* base, const Level& l, int planes, bool state_tile = false);
 // fused per level: pyrDown + pyrUp + subtract + dual-EMA update + gain (SpatialFilter.cpp:25-38,
 // TemporalFilter.cpp:9-22, MagnifyCore.hpp:127-134)
 cudaError_t launch_level(const LevelArgs& a, cudaStream_t s);

@@ -38,13 +38,17 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "MC_WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra MC_DONE_%=;\n\t"
-        "bra MC_WAIT_%=;\n\t"
-        "MC_DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+    // try_wait suspends the thread for a hardware-defined time slice per attempt; a copy that has not landed after
+    // 2^22 attempts (seconds) never will — trap so a bad descriptor surfaces as a launch error, not as a hung GPU.
+    unsigned ok = 0;
+    for (unsigned spin = 0; spin < (1u << 22); ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (ok) return;
+    }
+    __trap();
 }
 // 3-D tiled load {x, y, plane} -> shared; out-of-bounds elements are zero-filled by the TMA unit
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, int x, int y, int z, uint64_t* bar) {
@@ -166,12 +170,20 @@ struct LevelKArgs {
     int in_vec_ok;            // u8 rows are 4-byte aligned
 };
 
-template <int KIND, bool USE_TMA>
-__global__ void __launch_bounds__(256) k_level(const LevelKArgs a, const __grid_constant__ CUtensorMap tmap) {
+// PREFETCH (with USE_TMA): the tile's two state planes are requested as bulk-tensor copies at kernel entry, together
+// with the input window, and only waited for in the last phase — the fused kernel is latency-bound (B200 probe:
+// removing 16 % of its bytes did not shorten it), so what matters is how many bytes each CTA keeps in flight.
+template <int KIND, bool USE_TMA, bool PREFETCH>
+__global__ void __launch_bounds__(256) k_level(const LevelKArgs a, const __grid_constant__ CUtensorMap tmap,
+                                               const __grid_constant__ CUtensorMap tmap_hi,
+                                               const __grid_constant__ CUtensorMap tmap_lo) {
     __shared__ __align__(128) float sG[GH][GW];
     __shared__ __align__(16) float sH[GH][DP];
     __shared__ __align__(16) float sD[DH][DP];
+    __shared__ __align__(128) float sS[PREFETCH ? 2 : 1][PREFETCH ? TH : 1][PREFETCH ? TW : 4];   // hi / lo tiles
     __shared__ __align__(8) uint64_t tma_bar;
+    __shared__ __align__(8) uint64_t st_bar;
+    const bool prefetch = PREFETCH && a.band && !a.first;
     const int plane = blockIdx.z;
     const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
     const int wf = a.lf.w, hf = a.lf.h, wc = a.lc.w, hc = a.lc.h;
@@ -185,11 +197,19 @@ __global__ void __launch_bounds__(256) k_level(const LevelKArgs a, const __grid_
         // The (GH x GW) window of this plane is fetched by ONE bulk-tensor copy issued by one thread; the
         // TMA unit zero-fills whatever lies outside the level, and border tiles then patch those cells with
         // BORDER_REFLECT_101 copies taken from inside the window.
-        if (threadIdx.x == 0) mbar_init(&tma_bar, 1);
+        if (threadIdx.x == 0) {
+            mbar_init(&tma_bar, 1);
+            if (PREFETCH) mbar_init(&st_bar, 1);
+        }
         __syncthreads();
         if (threadIdx.x == 0) {
             mbar_expect_tx(&tma_bar, GH * GW * sizeof(float));
             tma_load_3d(&sG[0][0], &tmap, x0 - 4, y0 - 4, plane, &tma_bar);
+            if (prefetch) {
+                mbar_expect_tx(&st_bar, 2 * TH * TW * sizeof(float));
+                tma_load_3d(&sS[0][0][0], &tmap_hi, x0, y0, plane, &st_bar);
+                tma_load_3d(&sS[PREFETCH ? 1 : 0][0][0], &tmap_lo, x0, y0, plane, &st_bar);
+            }
         }
         mbar_wait(&tma_bar, 0);
         if (!interior) {
@@ -296,6 +316,7 @@ __global__ void __launch_bounds__(256) k_level(const LevelKArgs a, const __grid_
     float* __restrict__ lo = a.lo + (size_t)plane * a.lf.plane;
     float* __restrict__ m = a.m ? a.m + (size_t)plane * a.lf.plane : nullptr;
     const int gx = x0 + 4 * tx;
+    if (prefetch) mbar_wait(&st_bar, 0);   // every thread observes the copy's completion itself before reading sS
 #pragma unroll
     for (int ry = 0; ry < 2; ++ry) {
         const int gy = y0 + 2 * ty + ry;
@@ -309,8 +330,14 @@ __global__ void __launch_bounds__(256) k_level(const LevelKArgs a, const __grid_
             *reinterpret_cast<float4*>(hi + o) = b4;
             *reinterpret_cast<float4*>(lo + o) = b4;
         } else {
-            const float4 h4 = *reinterpret_cast<const float4*>(hi + o);
-            const float4 l4 = *reinterpret_cast<const float4*>(lo + o);
+            float4 h4, l4;
+            if (prefetch) {
+                h4 = *reinterpret_cast<const float4*>(&sS[0][PREFETCH ? 2 * ty + ry : 0][PREFETCH ? 4 * tx : 0]);
+                l4 = *reinterpret_cast<const float4*>(&sS[PREFETCH ? 1 : 0][PREFETCH ? 2 * ty + ry : 0][PREFETCH ? 4 * tx : 0]);
+            } else {
+                h4 = *reinterpret_cast<const float4*>(hi + o);
+                l4 = *reinterpret_cast<const float4*>(lo + o);
+            }
             float nh[4] = {h4.x, h4.y, h4.z, h4.w}, nl[4] = {l4.x, l4.y, l4.z, l4.w}, mm[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -812,7 +839,7 @@ inline unsigned cdiv(int a, int b) { return (unsigned)((a + b - 1) / b); }
 
 // Encodes a 3-D tiled tensor map {w, h, planes} over pitched f32 planes with the level kernel's box.
 // cuTensorMapEncodeTiled is resolved through the runtime so the library needs no link-time libcuda.
-bool make_level_tensor_map(void* out_map, const float* base, const Level& l, int planes) {
+bool make_level_tensor_map(void* out_map, const float* base, const Level& l, int planes, bool state_tile) {
     typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -828,7 +855,8 @@ bool make_level_tensor_map(void* out_map, const float* base, const Level& l, int
     }
     const cuuint64_t dims[3] = {(cuuint64_t)l.w, (cuuint64_t)l.h, (cuuint64_t)planes};
     const cuuint64_t strides[2] = {(cuuint64_t)l.pitch * sizeof(float), (cuuint64_t)l.plane * sizeof(float)};
-    const cuuint32_t box[3] = {(cuuint32_t)GW, (cuuint32_t)GH, 1u};
+    // input window (72 x 39, origin x0-4, y0-4) or state tile (64 x 32, origin x0, y0)
+    const cuuint32_t box[3] = {(cuuint32_t)(state_tile ? TW : GW), (cuuint32_t)(state_tile ? TH : GH), 1u};
     const cuuint32_t estr[3] = {1u, 1u, 1u};
     const CUresult r = encode(reinterpret_cast<CUtensorMap*>(out_map), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base),
                               dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
@@ -867,10 +895,14 @@ cudaError_t launch_level(const LevelArgs& a, cudaStream_t s) {
     k.in_vec_ok = a.in_kind == IN_U8 ? ((reinterpret_cast<uintptr_t>(a.g) % 4 == 0) && (a.in_row % 4 == 0) && (a.in_plane % 4 == 0)) : 1;
     dim3 grid(cdiv(a.lf.w, TW), cdiv(a.lf.h, TH), a.planes);
     static const CUtensorMap dummy{};
-    if (a.in_kind == IN_F32 && a.tmap) k_level<IN_F32, true><<<grid, 256, 0, s>>>(k, *reinterpret_cast<const CUtensorMap*>(a.tmap));
-    else if (a.in_kind == IN_F32) k_level<IN_F32, false><<<grid, 256, 0, s>>>(k, dummy);
-    else if (a.in_kind == IN_LAB16) k_level<IN_LAB16, false><<<grid, 256, 0, s>>>(k, dummy);
-    else k_level<IN_U8, false><<<grid, 256, 0, s>>>(k, dummy);
+    const CUtensorMap* tg = reinterpret_cast<const CUtensorMap*>(a.tmap);
+    if (a.in_kind == IN_F32 && tg && a.tmap_hi && a.tmap_lo)
+        k_level<IN_F32, true, true><<<grid, 256, 0, s>>>(k, *tg, *reinterpret_cast<const CUtensorMap*>(a.tmap_hi),
+                                                          *reinterpret_cast<const CUtensorMap*>(a.tmap_lo));
+    else if (a.in_kind == IN_F32 && tg) k_level<IN_F32, true, false><<<grid, 256, 0, s>>>(k, *tg, dummy, dummy);
+    else if (a.in_kind == IN_F32) k_level<IN_F32, false, false><<<grid, 256, 0, s>>>(k, dummy, dummy, dummy);
+    else if (a.in_kind == IN_LAB16) k_level<IN_LAB16, false, false><<<grid, 256, 0, s>>>(k, dummy, dummy, dummy);
+    else k_level<IN_U8, false, false><<<grid, 256, 0, s>>>(k, dummy, dummy, dummy);
     return cudaGetLastError();
 }
 

@@ -64,8 +64,14 @@ mc_status MotionMode::allocate(const ModeCtx& ctx, const FrameIO& io, int nlevel
     // TMA descriptors for the f32 inputs of the fused level kernels
     tmaps.assign((size_t)levels + 1, TensorMapStorage{});
     tmap_valid.assign((size_t)levels + 1, 0);
-    for (int l = 1; l < levels; ++l)
-        tmap_valid[(size_t)l] = make_level_tensor_map(&tmaps[(size_t)l], G[(size_t)l], lv[(size_t)l], (int)planes) ? 1 : 0;
+    tmaps_hi.assign((size_t)levels + 1, TensorMapStorage{});
+    tmaps_lo.assign((size_t)levels + 1, TensorMapStorage{});
+    for (int l = 1; l < levels; ++l) {
+        const Level& L = lv[(size_t)l];
+        tmap_valid[(size_t)l] = make_level_tensor_map(&tmaps[(size_t)l], G[(size_t)l], L, (int)planes) &&
+                                make_level_tensor_map(&tmaps_hi[(size_t)l], hi[(size_t)l], L, (int)planes, true) &&
+                                make_level_tensor_map(&tmaps_lo[(size_t)l], lo[(size_t)l], L, (int)planes, true) ? 1 : 0;
+    }
     if (channels == 3) {
         pitch16 = round_up(w, 64);
         plane16 = (size_t)h * pitch16;
@@ -111,7 +117,10 @@ mc_status MotionMode::process(const ModeCtx& ctx, const FrameIO& io, const mc_pa
             }
         } else {
             a.in_kind = 0; a.g = G[(size_t)l]; a.in_plane = lv[(size_t)l].plane; a.in_row = lv[(size_t)l].pitch;
-            if (tmap_valid[(size_t)l] && ctx.use_tma) a.tmap = &tmaps[(size_t)l];
+            if (tmap_valid[(size_t)l] && ctx.use_tma) {
+                a.tmap = &tmaps[(size_t)l];
+                if (ctx.prefetch_state) { a.tmap_hi = &tmaps_hi[(size_t)l]; a.tmap_lo = &tmaps_lo[(size_t)l]; }
+            }
         }
         a.channels = channels;
         a.lf = lv[(size_t)l]; a.lc = lv[(size_t)l + 1];

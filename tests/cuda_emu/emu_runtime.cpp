@@ -193,6 +193,10 @@ unsigned shfl(unsigned bits, int arg, int mode, int width) {
 
 // ---- bulk tensor (TMA) ---------------------------------------------------------------------------------
 void tma_load(void* dst, const CUtensorMap* tm, const int* c, uint64_t* bar) {
+    // hardware requirements on the operands of cp.async.bulk.tensor: 128-byte aligned shared destination,
+    // 64-byte aligned descriptor, 8-byte aligned mbarrier
+    if ((reinterpret_cast<uintptr_t>(dst) & 127) || (reinterpret_cast<uintptr_t>(tm) & 63) || (reinterpret_cast<uintptr_t>(bar) & 7))
+        die("misaligned TMA operand (shared destination 128 B, descriptor 64 B, mbarrier 8 B)", "bulk tensor load");
     const auto& m = tm->emu;
     const uint32_t rank = m.rank, es = m.elem_bytes;
     uint32_t box[5] = {1, 1, 1, 1, 1};
@@ -211,7 +215,36 @@ void tma_load(void* dst, const CUtensorMap* tm, const int* c, uint64_t* bar) {
             if (inb) std::memcpy(out, m.base + off, es); else std::memset(out, 0, es);
             out += es;
         }
-    *bar += 1;   // phase complete
+    size_t bytes = es;
+    for (uint32_t d = 0; d < rank; ++d) bytes *= box[d];
+    mbar_complete_tx(bar, (unsigned)bytes);
+}
+
+namespace {
+struct MbarState { unsigned arrivals_init = 1; long long pending_arrivals = 1, pending_tx = 0; };
+std::map<const uint64_t*, MbarState> g_mbars;
+void mbar_check(uint64_t* bar, MbarState& st) {
+    if (st.pending_arrivals <= 0 && st.pending_tx == 0) {   // phase completes; the barrier re-arms for the next one
+        *bar += 1;
+        st.pending_arrivals = st.arrivals_init;
+    }
+}
+}  // namespace
+
+void mbar_init(uint64_t* bar, unsigned arrivals) {
+    *bar = 0;
+    g_mbars[bar] = MbarState{arrivals, (long long)arrivals, 0};
+}
+void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    MbarState& st = g_mbars[bar];
+    st.pending_tx += bytes;
+    st.pending_arrivals -= 1;
+    mbar_check(bar, st);
+}
+void mbar_complete_tx(uint64_t* bar, unsigned bytes) {
+    MbarState& st = g_mbars[bar];
+    st.pending_tx -= bytes;
+    mbar_check(bar, st);
 }
 
 }  // namespace cuda_emu

@@ -29,8 +29,11 @@ namespace cuda_emu {
 // completes the mbarrier `bar` (one phase).
 void tma_load(void* dst, const CUtensorMap* tm, const int* coords, uint64_t* bar);
 void tma_store(const void* src, const CUtensorMap* tm, const int* coords);
-inline void mbar_init(uint64_t* bar, unsigned) { *bar = 0; }
-inline void mbar_expect_tx(uint64_t*, unsigned) {}
+// mbarrier with transaction counting: a phase completes when the expected arrivals have arrived AND the expected
+// bytes have landed (mbarrier.arrive.expect_tx / complete_tx).  *bar holds the number of completed phases.
+void mbar_init(uint64_t* bar, unsigned arrivals);
+void mbar_expect_tx(uint64_t* bar, unsigned bytes);        // one arrival + `bytes` expected
+void mbar_complete_tx(uint64_t* bar, unsigned bytes);      // what a finished bulk copy does
 inline void mbar_wait(uint64_t* bar, unsigned parity) {
     while (((*bar) & 1u) == parity) yield_spin();
 }

@@ -285,3 +285,21 @@ def test_band_from_state_option_equals_stored_band():
             _, oa = a.process_image(f, cfg)
             _, ob = b.process_image(f, cfg)
             assert np.array_equal(oa, ob), (w, h, t)
+
+
+def test_prefetch_state_option_equals_default():
+    """Option prefetch_state (the level kernel requests its hi / lo tiles by TMA at kernel entry and reads them from
+    shared memory in the last phase) must not change a single bit of the output or of the state, ragged borders
+    included."""
+    for (w, h, c, lv) in [(640, 480, 3, 4), (333, 251, 1, 5), (131, 75, 3, 3)]:
+        cfg, _ = make_cfgs(O.MODE_LAPLACE, 20, 50.0, 0.4, 3.0, 30, lv)
+        a, b = L.MagnificationProcessor(0), L.MagnificationProcessor(0)
+        b.set_option("prefetch_state", 1)
+        for t in range(5):
+            f = synth_frame(t, w, h, c)
+            _, oa = a.process_image(f, cfg)
+            _, ob = b.process_image(f, cfg)
+            assert np.array_equal(oa, ob), (w, h, t)
+        for lvl in range(1, lv):
+            for name in ("lowpassHi", "lowpassLo"):
+                assert np.array_equal(a.get_state(name, lvl), b.get_state(name, lvl)), (w, h, lvl, name)
