@@ -160,6 +160,8 @@ void* mc_stream(mc_handle* h);
  *   "prefetch_state" (default 0; needs use_tma): the fused level kernel requests the tile's two state planes as TMA
  *        bulk copies at kernel entry, together with its input window, instead of loading them in its last phase
  *        (same results; for A/B measurements — the kernel is latency-bound)
+ *   "egress_tma" (default 0; needs use_tma; 3-channel frames): the egress kernel requests its Lab16 tile, its level-1
+ *        band window and its level-2 window as TMA bulk copies at kernel entry (same results; for A/B measurements)
  *   "analysis_only" (default 0): Laplace only — frames after the first update the temporal state but skip
  *        synthesis and egress and report *produced = 0; the cheap first pass of temporal sharding
  *   "band_from_state" (default 0): Laplace synthesis rebuilds each amplified band gain*(hi-lo) from the two

@@ -79,6 +79,11 @@ mc_status MotionMode::allocate(const ModeCtx& ctx, const FrameIO& io, int nlevel
         MCK(arena.alloc_bytes(&p, planes * plane16 * sizeof(int16_t)));
         lab16 = (int16_t*)p;
     }
+    // TMA descriptors of the egress kernel's three tile sources (option egress_tma; 3 channels, stored band)
+    egress_maps = EgressMaps{};
+    if (channels == 3 && !from_state && levels >= 2 && M[1])
+        make_egress_tensor_maps(egress_maps, lab16, w, h, pitch16, plane16, M[1], lv[1], levels >= 3 ? M[2] : nullptr, lv[2 <= levels ? 2 : 0],
+                                (int)planes);
     allocated = true;
     return MC_OK;
 }
@@ -160,7 +165,8 @@ mc_status MotionMode::process(const ModeCtx& ctx, const FrameIO& io, const mc_pa
     }
     const Level& l1 = lv[levels >= 1 ? 1 : 0];
     const Level& l2 = lv[levels >= 2 ? 2 : 0];
-    LAUNCH("egress", 0, launch_egress(io, *ctx.tables, lab16, pitch16, plane16, m1, l1, c2, l2, (float)p.chromAttenuation, ctx.float_out, ctx.stream));
+    LAUNCH("egress", 0, launch_egress(io, *ctx.tables, lab16, pitch16, plane16, m1, l1, c2, l2, (float)p.chromAttenuation, ctx.float_out,
+                                      ctx.stream, ctx.egress_tma && ctx.use_tma ? &egress_maps : nullptr));
     empty = false;
     *produced = 1;
     return MC_OK;

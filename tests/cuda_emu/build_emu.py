@@ -80,7 +80,7 @@ def rewrite_launches(src: str) -> str:
         assert src[lp] == "(", f"launch of {kernel}: expected '(' after >>>"
         rp = _match_paren(src, lp)
         args = src[lp + 1:rp]
-        name = re.sub(r"<.*", "", kernel)
+        name = " ".join(kernel.split())   # keeps the template arguments: visible with CUDA_EMU_TRACE=1
         out.append(src[pos:b])
         out.append(f'cuda_emu::Launcher({cfg}).run("{name}", [&]() {{ {kernel}({args}); }})')
         pos = rp + 1

@@ -143,6 +143,8 @@ void launch(dim3 grid, dim3 block, size_t, void*, const char* name, const std::f
     if (g_fibers.size() < n) g_fibers.resize(n);
     for (unsigned t = 0; t < n; ++t)
         if (!g_fibers[t].stack) g_fibers[t].stack = static_cast<char*>(std::malloc(kStack));
+    static const bool trace = std::getenv("CUDA_EMU_TRACE") != nullptr;
+    if (trace) std::fprintf(stderr, "cuda_emu: launch %s grid (%u,%u,%u) block (%u,%u,%u)\n", name, grid.x, grid.y, grid.z, block.x, block.y, block.z);
     g_in_kernel = true;
     g_body = &body;
     gridDim = grid;

@@ -303,3 +303,18 @@ def test_prefetch_state_option_equals_default():
         for lvl in range(1, lv):
             for name in ("lowpassHi", "lowpassLo"):
                 assert np.array_equal(a.get_state(name, lvl), b.get_state(name, lvl)), (w, h, lvl, name)
+
+
+def test_egress_tma_option_equals_default():
+    """Option egress_tma (Lab16 tile, level-1 band window and level-2 window fetched as TMA bulk copies, border rule
+    applied to window indices) must not change a single bit — interior tiles, ragged borders, 2 and 3 levels (no /
+    top-band level-2 window) and the first frame (no motion) included."""
+    for (w, h, lv) in [(640, 480, 4), (333, 251, 5), (131, 75, 3), (200, 120, 2), (64, 48, 6)]:
+        cfg, _ = make_cfgs(O.MODE_LAPLACE, 20, 50.0, 0.4, 3.0, 30, lv)
+        a, b = L.MagnificationProcessor(0), L.MagnificationProcessor(0)
+        b.set_option("egress_tma", 1)
+        for t in range(4):
+            f = synth_frame(t, w, h, 3)
+            _, oa = a.process_image(f, cfg)
+            _, ob = b.process_image(f, cfg)
+            assert np.array_equal(oa, ob), (w, h, lv, t)

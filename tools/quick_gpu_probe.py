@@ -1,7 +1,12 @@
 #!/usr/bin/env python
 """Torch-free GPU probe (seconds, for tight gpurun budgets): parity of the Laplace path against the checker on a
 small and a 1080p clip, then the per-kernel device-time table (profile_kernels) of the 1080p bench workload through
-the blocking host API.  Prints one JSON line."""
+the blocking host API.  Prints one JSON line.
+
+    python tools/quick_gpu_probe.py                 # parity + one table (PROBE_LANES, default 8)
+    python tools/quick_gpu_probe.py --ab 8,32       # A/B of the kernel options at those lane counts:
+                                                    # default | prefetch_state | egress_tma | both | band_from_state | ...
+"""
 import json
 import os
 import sys
@@ -36,22 +41,33 @@ def main():
             worst, ndiff = max(worst, int(d.max())), ndiff + int((d > 0).sum())
         out[f"parity_{w}x{h}"] = {"max_u8_diff": worst, "differing": ndiff, "checker": "reference" if R is not None else "oracle"}
         proc.close()
-    lanes = int(os.environ.get("PROBE_LANES", "8"))
     cfg, _ = make_cfgs(O.MODE_LAPLACE, 20, 50.0, 0.4, 3.0, 0, 6)
     base = [synth_frame(t, 1920, 1080, 3) for t in range(2)]
-    clip = [np.stack([np.roll(base[t], (11 * k, 37 * k), axis=(0, 1)) for k in range(lanes)]) for t in range(2)]
-    proc = L.MagnificationProcessor(0, lanes=lanes)
-    for i in range(3):
-        proc.process_image(clip[i % 2], cfg)
-    proc.set_option("profile_kernels", 1)
-    for i in range(8):
-        proc.process_image(clip[i % 2], cfg)
-    prof = proc.profile_read()
-    table = sorted(((f"{k}[{lvl}]", tms / n * 1e3) for (k, lvl), (n, tms) in prof.items()), key=lambda r: -r[1])
-    out["lanes"] = lanes
-    out["kernels_us"] = {k: round(us, 1) for k, us in table}
-    out["step_us"] = round(sum(us for _, us in table), 1)
-    out["fps_device_kernels_only"] = round(lanes / (out["step_us"] * 1e-6), 1)
+
+    def table_for(lanes, options):
+        clip = [np.stack([np.roll(base[t], (11 * k, 37 * k), axis=(0, 1)) for k in range(lanes)]) for t in range(2)]
+        proc = L.MagnificationProcessor(0, lanes=lanes)
+        for k, v in options.items():
+            proc.set_option(k, v)
+        for i in range(3):
+            proc.process_image(clip[i % 2], cfg)
+        proc.set_option("profile_kernels", 1)
+        for i in range(8):
+            proc.process_image(clip[i % 2], cfg)
+        prof = proc.profile_read()
+        proc.close()
+        table = sorted(((f"{k}[{lvl}]", tms / n * 1e3) for (k, lvl), (n, tms) in prof.items()), key=lambda r: -r[1])
+        step = sum(us for _, us in table)
+        return {"lanes": lanes, "options": options, "kernels_us": {k: round(us, 1) for k, us in table},
+                "step_us": round(step, 1), "fps_device_kernels_only": round(lanes / (step * 1e-6), 1)}
+
+    if "--ab" in sys.argv:
+        lane_list = [int(x) for x in sys.argv[sys.argv.index("--ab") + 1].split(",")]
+        out["ab"] = [table_for(n, o) for n in lane_list
+                     for o in ({}, {"prefetch_state": 1}, {"egress_tma": 1}, {"prefetch_state": 1, "egress_tma": 1},
+                               {"band_from_state": 1}, {"prefetch_state": 1, "band_from_state": 1})]
+    else:
+        out.update(table_for(int(os.environ.get("PROBE_LANES", "8")), {}))
     out["seconds"] = round(time.time() - t00, 1)
     print(json.dumps(out))
 
