@@ -160,6 +160,9 @@ void* mc_stream(mc_handle* h);
  *   "prefetch_state" (default 0; needs use_tma): the fused level kernel requests the tile's two state planes as TMA
  *        bulk copies at kernel entry, together with its input window, instead of loading them in its last phase
  *        (same results; for A/B measurements — the kernel is latency-bound)
+ *   "use_tail" (default 0): Laplace — the coarse pyramid levels whose planes together fit one CTA's shared memory
+ *        (levels >= 3 at 1080p) are analysed, filtered and collapsed by one kernel launch instead of one launch per
+ *        level and direction (results within float rounding of the per-level kernels; for A/B measurements)
  *   "egress_tma" (default 0; needs use_tma; 3-channel frames): the egress kernel requests its Lab16 tile, its level-1
  *        band window and its level-2 window as TMA bulk copies at kernel entry (same results; for A/B measurements)
  *   "analysis_only" (default 0): Laplace only — frames after the first update the temporal state but skip

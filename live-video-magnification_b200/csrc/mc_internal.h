@@ -120,6 +120,26 @@ cudaError_t launch_egress(const FrameIO& io, const DeviceTables& tb, const int16
                           const BandSrc& m1, const Level& l1, const BandSrc& c2, const Level& l2, float chroma,
                           float* float_out_or_null, cudaStream_t s, const EgressMaps* maps = nullptr);
 
+// The coarse end of the pyramid in one launch (option use_tail): band levels t .. t+n-1 (lv[0..n-1]) plus the plane
+// above them (lv[n]) stay resident in one CTA's shared memory per plane; see k_tail.
+constexpr int kTailMaxLevels = 8;
+constexpr size_t kTailSmemBudget = 200 * 1024;
+struct TailArgs {
+    int n = 0;
+    Level lv[kTailMaxLevels + 1];
+    int soff[kTailMaxLevels + 1] = {};
+    const float* g = nullptr;                        // G_t planes
+    float* hi[kTailMaxLevels] = {};
+    float* lo[kTailMaxLevels] = {};
+    float gain[kTailMaxLevels] = {};
+    float* cur_out = nullptr;                        // cur_t planes (null: analysis only)
+    float* g_last = nullptr;                         // G_{t+n} planes (null: not kept)
+    int first = 0;
+    double c_hi = 0, omc_hi = 0, c_lo = 0, omc_lo = 0;
+};
+size_t tail_smem_bytes(const Level* lv, int n);
+cudaError_t launch_tail(TailArgs& a, int planes, cudaStream_t s);
+
 // PreprocessProcessor + GrayscaleProcessor on the device (mc_preprocess.cu)
 cudaError_t launch_preprocess(const uint8_t* src_roi, size_t step, int cn, int sw, int sh, int dw, int dh, bool copy_only,
                               const AreaTap* xtab, const int* xofs, const AreaTap* ytab, const int* yofs, uint8_t* dst,

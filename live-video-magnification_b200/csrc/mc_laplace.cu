@@ -876,6 +876,109 @@ __global__ void __launch_bounds__(256) k_egress(const EgressArgs a, const __grid
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// tail: the coarse end of the pyramid in ONE launch (option use_tail).  Levels >= 3 of a 1080p frame hold a few
+// thousand pixels each; as separate launches they cost ~10 us apiece for microseconds of work.  Here one CTA owns
+// one plane (lane x channel) and keeps its levels t .. L resident in shared memory (at most ~200 KB, unpadded
+// rows): for each level pyrDown, band = G - pyrUp(G_next), both EMA updates (the only HBM traffic besides the
+// input plane), gain; then the collapse up to cur_t, which is the only plane written back.  Same arithmetic and
+// operation order as k_level / k_collapse (cv::pyrDown / pyrUp border rules applied to indices).
+// ------------------------------------------------------------------------------------------------
+#if defined(MC_CUDA_EMU)
+#define MC_DYN_SMEM(name) float* name = static_cast<float*>(cuda_emu::dyn_smem())
+#else
+#define MC_DYN_SMEM(name) extern __shared__ __align__(16) float name[]
+#endif
+
+__device__ __forceinline__ float tail_pyrup_at(const float* __restrict__ c, int wc, int hc, int y, int x) {
+    const int i = x >> 1, j = y >> 1;
+    const int im = upsrc(i - 1, wc), ip = upsrc(i + 1, wc);
+    const bool xodd = x & 1, yodd = y & 1;
+    float r[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        const float* row = c + upsrc(j - 1 + q, hc) * wc;
+        r[q] = xodd ? (row[i] + row[ip]) * 4.0f : (row[im] + row[i] * 6.0f + row[ip]);
+    }
+    return yodd ? ((r[1] + r[2]) * 4.0f) * kInv64 : (r[0] + r[1] * 6.0f + r[2]) * kInv64;
+}
+
+__global__ void __launch_bounds__(1024) k_tail(const TailArgs a) {
+    MC_DYN_SMEM(S);
+    const int plane = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    {
+        const Level L0 = a.lv[0];
+        const float* __restrict__ src = a.g + (size_t)plane * L0.plane;
+        float* dst = S + a.soff[0];
+        for (int y = warp; y < L0.h; y += nw)
+            for (int x = lane; x < L0.w; x += 32) dst[y * L0.w + x] = __ldg(src + (size_t)y * L0.pitch + x);
+    }
+    __syncthreads();
+    for (int l = 0; l < a.n; ++l) {
+        const Level F = a.lv[l], C = a.lv[l + 1];
+        float* f = S + a.soff[l];
+        float* c = S + a.soff[l + 1];
+        // pyrDown: row pass of the five source rows, then the column pass (same order as k_level)
+        for (int y = warp; y < C.h; y += nw)
+            for (int x = lane; x < C.w; x += 32) {
+                const int x0 = reflect101(2 * x - 2, F.w), x1 = reflect101(2 * x - 1, F.w), x2 = 2 * x,
+                          x3 = reflect101(2 * x + 1, F.w), x4 = reflect101(2 * x + 2, F.w);
+                float hr[5];
+#pragma unroll
+                for (int q = 0; q < 5; ++q) {
+                    const float* p = f + reflect101(2 * y - 2 + q, F.h) * F.w;
+                    hr[q] = down5(p[x0], p[x1], p[x2], p[x3], p[x4]);
+                }
+                c[y * C.w + x] = down5(hr[0], hr[1], hr[2], hr[3], hr[4]) * kInv256;
+            }
+        __syncthreads();
+        // band + temporal filter; the amplified band replaces G_l in shared memory
+        float* __restrict__ hi = a.hi[l] + (size_t)plane * F.plane;
+        float* __restrict__ lo = a.lo[l] + (size_t)plane * F.plane;
+        const float gain = a.gain[l];
+        for (int y = warp; y < F.h; y += nw)
+            for (int x = lane; x < F.w; x += 32) {
+                const float band = f[y * F.w + x] - tail_pyrup_at(c, C.w, C.h, y, x);
+                const size_t o = (size_t)y * F.pitch + x;
+                if (a.first) {
+                    hi[o] = band;
+                    lo[o] = band;
+                } else {
+                    const float nh = ema(hi[o], band, a.omc_hi, a.c_hi), nl = ema(lo[o], band, a.omc_lo, a.c_lo);
+                    hi[o] = nh;
+                    lo[o] = nl;
+                    f[y * F.w + x] = (nh - nl) * gain;
+                }
+            }
+        __syncthreads();
+    }
+    if (a.g_last) {   // G_{t+n}: the residual level (kept for the faithful option's state copy)
+        const Level R = a.lv[a.n];
+        const float* src = S + a.soff[a.n];
+        float* dst = a.g_last + (size_t)plane * R.plane;
+        for (int y = warp; y < R.h; y += nw)
+            for (int x = lane; x < R.w; x += 32) dst[(size_t)y * R.pitch + x] = src[y * R.w + x];
+    }
+    if (a.first || !a.cur_out) return;
+    // collapse: cur_{top} = m_{top} (the residual above it is zeroed, MagnifyCore.hpp:130-131), cur_l = pyrUp(cur_{l+1}) + m_l
+    for (int l = a.n - 2; l >= 0; --l) {
+        const Level F = a.lv[l], C = a.lv[l + 1];
+        float* f = S + a.soff[l];
+        const float* c = S + a.soff[l + 1];
+        for (int y = warp; y < F.h; y += nw)
+            for (int x = lane; x < F.w; x += 32) f[y * F.w + x] = tail_pyrup_at(c, C.w, C.h, y, x) + f[y * F.w + x];
+        __syncthreads();
+    }
+    {
+        const Level L0 = a.lv[0];
+        const float* src = S + a.soff[0];
+        float* dst = a.cur_out + (size_t)plane * L0.plane;
+        for (int y = warp; y < L0.h; y += nw)
+            for (int x = lane; x < L0.w; x += 32) dst[(size_t)y * L0.pitch + x] = src[y * L0.w + x];
+    }
+}
+
 __global__ void k_copy(float* __restrict__ dst, const float* __restrict__ src, size_t n) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
         dst[i] = src[i];
@@ -1025,6 +1128,29 @@ cudaError_t launch_egress(const FrameIO& io, const DeviceTables& tb, const int16
                                                      *reinterpret_cast<const CUtensorMap*>(&maps->c2));
     else if (io.channels == 3) k_egress<3, false><<<grid, 256, 0, s>>>(a, dummy, dummy, dummy);
     else k_egress<1, false><<<grid, 256, 0, s>>>(a, dummy, dummy, dummy);
+    return cudaGetLastError();
+}
+
+size_t tail_smem_bytes(const Level* lv, int n) {
+    size_t floats = 0;
+    for (int l = 0; l <= n; ++l) floats += ((size_t)lv[l].w * lv[l].h + 3) / 4 * 4;
+    return floats * sizeof(float);
+}
+
+cudaError_t launch_tail(TailArgs& a, int planes, cudaStream_t s) {
+    int off = 0;
+    for (int l = 0; l <= a.n; ++l) {
+        a.soff[l] = off;
+        off += (a.lv[l].w * a.lv[l].h + 3) / 4 * 4;
+    }
+    const size_t bytes = (size_t)off * sizeof(float);
+    static size_t configured = 0;
+    if (bytes > configured) {   // opt in to > 48 KB of dynamic shared memory (once per size increase)
+        cudaError_t e = cudaFuncSetAttribute(k_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e != cudaSuccess) return e;
+        configured = bytes;
+    }
+    k_tail<<<planes, 1024, bytes, s>>>(a);
     return cudaGetLastError();
 }
 

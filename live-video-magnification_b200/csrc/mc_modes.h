@@ -37,6 +37,8 @@ struct ModeCtx {
     bool use_tma;      // stage level-kernel tiles with cp.async.bulk.tensor (option "use_tma", default on)
     bool prefetch_state;    // level kernel requests its state tiles by TMA at kernel entry (option "prefetch_state", default off
                             // until measured on the B200)
+    bool use_tail;          // levels >= MotionMode::tail_start run in the single fused tail kernel (option "use_tail", default off
+                            // until measured on the B200)
     bool egress_tma;        // egress requests its three tile sources by TMA at kernel entry (option "egress_tma", default off
                             // until measured on the B200)
     bool band_from_state;   // synthesis rebuilds gain*(hi-lo) from the state planes instead of reading a stored band
@@ -95,6 +97,7 @@ struct MotionMode {
     DeviceArena arena;
 
     std::vector<TensorMapStorage> tmaps;   // per level: TMA descriptor of G[l] (tmap_valid[l] != 0)
+    int tail_start = 0;                    // first level of the fused tail kernel (0: none fits), option use_tail
     EgressMaps egress_maps;                // TMA descriptors of the egress kernel's tile sources (option egress_tma)
     std::vector<TensorMapStorage> tmaps_hi, tmaps_lo;   // ... and of the state planes (64 x 32 tiles, option prefetch_state)
     std::vector<char> tmap_valid;

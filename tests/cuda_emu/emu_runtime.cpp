@@ -135,8 +135,13 @@ void run_block(unsigned n, const char* name) {
 
 }  // namespace
 
-void launch(dim3 grid, dim3 block, size_t, void*, const char* name, const std::function<void()>& body) {
+namespace { void* g_dyn_smem = nullptr; }
+void* dyn_smem() { return g_dyn_smem; }
+
+void launch(dim3 grid, dim3 block, size_t smem, void*, const char* name, const std::function<void()>& body) {
     if (g_in_kernel) die("nested launch", name);
+    if (smem > 227 * 1024) die("more than 227 KB of dynamic shared memory", name);
+    g_dyn_smem = smem ? std::aligned_alloc(128, (smem + 127) / 128 * 128) : nullptr;   // fresh per launch: ASan sees overruns
     const unsigned n = block.x * block.y * block.z;
     if (n == 0 || n > 1024) die("bad block size", name);
     if (grid.x == 0 || grid.y == 0 || grid.z == 0 || grid.y > 65535 || grid.z > 65535) die("bad grid size", name);
@@ -158,6 +163,8 @@ void launch(dim3 grid, dim3 block, size_t, void*, const char* name, const std::f
             }
     g_in_kernel = false;
     g_cur = -1;
+    std::free(g_dyn_smem);
+    g_dyn_smem = nullptr;
 }
 
 void sync_threads() {

@@ -74,6 +74,7 @@ void sync_threads();
 unsigned shfl(unsigned value_bits, int src_lane_or_delta, int mode, int width);   // mode 0 idx, 1 up, 2 down, 3 xor
 void yield_spin();   // a thread polling a flag another thread of the CTA will set
 unsigned lane_id();
+void* dyn_smem();    // the launch's dynamic shared memory (`extern __shared__`), 128-byte aligned
 }  // namespace cuda_emu
 
 typedef struct CUstream_st* cudaStream_t;
@@ -173,6 +174,10 @@ constexpr unsigned cudaEventDisableTiming = 2, cudaEventDefault = 0;
 constexpr unsigned cudaHostAllocDefault = 0, cudaHostRegisterDefault = 0;
 constexpr unsigned long long cudaEnableDefault = 0;
 
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8, cudaFuncAttributePreferredSharedMemoryCarveout = 9 };
+template <typename F> inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int value) {
+    return value <= 227 * 1024 ? cudaSuccess : cudaErrorInvalidValue;   // sm_100: at most 227 KB per CTA
+}
 const char* cudaGetErrorString(cudaError_t e);
 cudaError_t cudaGetLastError();
 cudaError_t cudaPeekAtLastError();

@@ -318,3 +318,55 @@ def test_egress_tma_option_equals_default():
             _, oa = a.process_image(f, cfg)
             _, ob = b.process_image(f, cfg)
             assert np.array_equal(oa, ob), (w, h, lv, t)
+
+
+@pytest.mark.parametrize("w,h,c,levels", [(640, 480, 3, 4), (322, 241, 3, 5), (333, 251, 1, 6), (1920, 1080, 3, 6), (200, 120, 3, 3)])
+def test_fused_tail_option(w, h, c, levels):
+    """Option use_tail: the coarse levels (all whose planes fit one CTA's shared memory) run in ONE kernel instead of
+    one launch per level and direction.  Parity with the oracle as for the default path (f32 < 1e-4, <= 1 LSB), state
+    planes included, and agreement with the default path to float rounding; fewer launches per frame."""
+    cfg, ocfg = make_cfgs(O.MODE_LAPLACE, 20, 50.0, 0.4, 3.0, 30, levels)
+    a, b, oproc = L.MagnificationProcessor(0), L.MagnificationProcessor(0), O.MagnificationProcessor()
+    b.set_option("use_tail", 1)
+    b.set_option("keep_float_output", 1)
+    n = 3 if w > 1000 else 6
+    for t in range(n):
+        f = synth_frame(t, w, h, c)
+        dbg = {}
+        _, oa = a.process_image(f, cfg)
+        _, ob = b.process_image(f, cfg)
+        _, oo = oproc.process(f, ocfg, dbg)
+        d = u8_diff(oa, ob)
+        assert int(d.max()) <= 1 and float((d == 0).mean()) >= 0.9999, (t, int(d.max()))
+        assert int(u8_diff(ob, oo).max()) <= 1, t
+        ref_f = dbg["output_bgr_f32"] if c == 3 else dbg["output_f32"]
+        got_f = b.float_output(w, h, c)[0]
+        assert float(np.abs((got_f[..., 0] if c == 1 else got_f) - ref_f).max()) < F32_TOL, t
+    lv_eff = min(levels, L.calculateMaxLevels(w, h))
+    for lvl in range(1, lv_eff):
+        for name, ost in (("lowpassHi", oproc.motion.lowpassHi), ("lowpassLo", oproc.motion.lowpassLo)):
+            got, ref = b.get_state(name, lvl)[0], planar(ost[lvl])
+            assert float(np.abs(got - ref).max()) < 1e-3, (name, lvl)
+    if levels >= 4:
+        assert b.launch_count < a.launch_count
+
+
+@pytest.mark.parametrize("opts", [("use_tail", "prefetch_state", "egress_tma"), ("use_tail", "band_from_state", "prefetch_state"),
+                                  ("use_tail", "faithful_level0"), ("prefetch_state", "egress_tma")])
+def test_option_combinations_agree_with_default(opts):
+    """The A/B options compose: any combination gives the default path's frames (bit-identical without the fused
+    tail, to float rounding with it), over the first frame, ragged borders and a parameter change."""
+    w, h, levels = 333, 251, 5
+    a, b = L.MagnificationProcessor(0), L.MagnificationProcessor(0)
+    for k in opts:
+        b.set_option(k, 1)
+    for t in range(6):
+        cfg, _ = make_cfgs(O.MODE_LAPLACE, 20 if t < 4 else 35, 50.0, 0.4, 3.0, 30, levels)
+        f = synth_frame(t, w, h, 3)
+        _, oa = a.process_image(f, cfg)
+        _, ob = b.process_image(f, cfg)
+        d = u8_diff(oa, ob)
+        if "use_tail" in opts:
+            assert int(d.max()) <= 1 and float((d == 0).mean()) >= 0.9999, (opts, t)
+        else:
+            assert int(d.max()) == 0, (opts, t)
