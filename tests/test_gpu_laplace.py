@@ -287,6 +287,7 @@ def test_band_from_state_option_equals_stored_band():
             assert np.array_equal(oa, ob), (w, h, t)
 
 
+@pytest.mark.experimental
 def test_prefetch_state_option_equals_default():
     """Option prefetch_state (the level kernel requests its hi / lo tiles by TMA at kernel entry and reads them from
     shared memory in the last phase) must not change a single bit of the output or of the state, ragged borders
@@ -305,6 +306,7 @@ def test_prefetch_state_option_equals_default():
                 assert np.array_equal(a.get_state(name, lvl), b.get_state(name, lvl)), (w, h, lvl, name)
 
 
+@pytest.mark.experimental
 def test_egress_tma_option_equals_default():
     """Option egress_tma (Lab16 tile, level-1 band window and level-2 window fetched as TMA bulk copies, border rule
     applied to window indices) must not change a single bit — interior tiles, ragged borders, 2 and 3 levels (no /
@@ -320,6 +322,7 @@ def test_egress_tma_option_equals_default():
             assert np.array_equal(oa, ob), (w, h, lv, t)
 
 
+@pytest.mark.experimental
 @pytest.mark.parametrize("w,h,c,levels", [(640, 480, 3, 4), (322, 241, 3, 5), (333, 251, 1, 6), (1920, 1080, 3, 6), (200, 120, 3, 3)])
 def test_fused_tail_option(w, h, c, levels):
     """Option use_tail: the coarse levels (all whose planes fit one CTA's shared memory) run in ONE kernel instead of
@@ -351,6 +354,7 @@ def test_fused_tail_option(w, h, c, levels):
         assert b.launch_count < a.launch_count
 
 
+@pytest.mark.experimental
 @pytest.mark.parametrize("opts", [("use_tail", "prefetch_state", "egress_tma"), ("use_tail", "band_from_state", "prefetch_state"),
                                   ("use_tail", "faithful_level0"), ("prefetch_state", "egress_tma")])
 def test_option_combinations_agree_with_default(opts):
