@@ -179,9 +179,11 @@ MC_HD void lab_to_bgr(float L, float a, float b, const LabInvCoeffs& k, const fl
     float vb = k.c[0] * X + k.c[1] * Y + k.c[2] * Z;
     float vg = k.c[3] * X + k.c[4] * Y + k.c[5] * Z;
     float vr = k.c[6] * X + k.c[7] * Y + k.c[8] * Z;
-    vb = fminf(fmaxf(vb, 0.0f), 1.0f);
-    vg = fminf(fmaxf(vg, 0.0f), 1.0f);
-    vr = fminf(fmaxf(vr, 0.0f), 1.0f);
+    // OpenCV clips as max(min(v, 1), 0) with SSE operand rules, so a NaN (Riesz: 0/0 in flat regions)
+    // comes out as 1.0 — white — not 0; fminf/fmaxf return the non-NaN operand, which gives exactly that
+    vb = fmaxf(fminf(vb, 1.0f), 0.0f);
+    vg = fmaxf(fminf(vg, 1.0f), 0.0f);
+    vr = fmaxf(fminf(vr, 1.0f), 0.0f);
     ob = inv_gamma(vb, gtab);
     og = inv_gamma(vg, gtab);
     orr = inv_gamma(vr, gtab);
@@ -200,6 +202,10 @@ __device__ __forceinline__ float mc_lg2(float x) { float y; asm("lg2.approx.ftz.
 __device__ __forceinline__ float mc_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 #endif
 
+// NAN_AS_OPENCV: clip as OpenCV does (max(min(v, 1), 0): NaN -> 1.0, white).  Phase (Riesz) needs it — its L plane is
+// NaN wherever the blurred amplitude is 0, e.g. in letterbox bars — Motion (Laplace) cannot produce a NaN and keeps
+// the clip folded into the FFMA (.SAT, NaN -> 0) of its issue-bound egress kernel.
+template <bool NAN_AS_OPENCV = false>
 __device__ __forceinline__ void lab_to_bgr_fast(float L, float a, float b, const LabInvCoeffs& k,
                                                 const float4* __restrict__ gtab, float& ob, float& og, float& orr) {
     const float y_lin = L * (1.0f / 903.3f);
@@ -213,9 +219,14 @@ __device__ __forceinline__ void lab_to_bgr_fast(float L, float a, float b, const
     const float fth = 6.0f / 29.0f;
     const float X = fx <= fth ? (fx - 16.0f / 116.0f) * (1.0f / 7.787f) : fx * fx * fx;
     const float Z = fz <= fth ? (fz - 16.0f / 116.0f) * (1.0f / 7.787f) : fz * fz * fz;
-    const float vb = __saturatef(k.c[0] * X + k.c[1] * Y + k.c[2] * Z);
-    const float vg = __saturatef(k.c[3] * X + k.c[4] * Y + k.c[5] * Z);
-    const float vr = __saturatef(k.c[6] * X + k.c[7] * Y + k.c[8] * Z);
+    float vb = k.c[0] * X + k.c[1] * Y + k.c[2] * Z;
+    float vg = k.c[3] * X + k.c[4] * Y + k.c[5] * Z;
+    float vr = k.c[6] * X + k.c[7] * Y + k.c[8] * Z;
+    if (NAN_AS_OPENCV) {
+        vb = fmaxf(fminf(vb, 1.0f), 0.0f); vg = fmaxf(fminf(vg, 1.0f), 0.0f); vr = fmaxf(fminf(vr, 1.0f), 0.0f);
+    } else {
+        vb = __saturatef(vb); vg = __saturatef(vg); vr = __saturatef(vr);
+    }
     ob = fmaf(1.055f, mc_ex2(mc_lg2(vb) * (1.0f / 2.4f)), -0.055f);
     og = fmaf(1.055f, mc_ex2(mc_lg2(vg) * (1.0f / 2.4f)), -0.055f);
     orr = fmaf(1.055f, mc_ex2(mc_lg2(vr) * (1.0f / 2.4f)), -0.055f);

@@ -410,7 +410,7 @@ __global__ void __launch_bounds__(256) k_riesz_egress(const float* __restrict__ 
     const float A = fmaf((float)p[plane16], 1.0f / 64.0f, -128.0f);
     const float B = fmaf((float)p[2 * plane16], 1.0f / 64.0f, -128.0f);
     float ob, og, orr;
-    lab_to_bgr_fast(L, A, B, coeffs, gtab, ob, og, orr);
+    lab_to_bgr_fast<true>(L, A, B, coeffs, gtab, ob, og, orr);   // NaN L (flat regions) -> white, as OpenCV
     uint8_t* q = out + (size_t)lane * lane_stride + (size_t)y * step + (size_t)x * 3;
     q[0] = unit_to_u8(ob); q[1] = unit_to_u8(og); q[2] = unit_to_u8(orr);
     if (fout) {

@@ -142,3 +142,34 @@ def test_riesz_lanes_match_single():
         if pm:
             for k in range(2):
                 assert np.array_equal(mo[k], outs[k][1]), (t, k)
+
+
+def test_flat_regions_nan_semantics_match_the_reference():
+    """Letterbox bars / black or flat frames: the blurred amplitude is exactly 0 there, the reference divides 0/0
+    (RieszPyramid.cpp:125-126, SURVEY A.6-9), the NaN survives cosSin and the collapse, and cv::cvtColor(Lab2BGR) clips it to
+    1.0 — the bars come out WHITE.  The device path must reproduce exactly that (same NaN region, same mapping)."""
+    w, h, levels = 192, 128, 4
+    cfg, ocfg = make_cfgs(O.MODE_PHASE, 50, 50.0, 0.4, 3.0, 0, levels)
+    rng = np.random.default_rng(3)
+
+    def letterbox(t):
+        f = np.zeros((h, w, 3), np.uint8)
+        f[32:96] = synth_frame(t, w, 64, 3)
+        return f
+
+    clips = {"letterbox": [letterbox(t) for t in range(5)],
+             "black": [np.zeros((h, w, 3), np.uint8) for _ in range(3)],
+             "flat+noise block": [np.full((h, w, 3), 128, np.uint8) for _ in range(3)]}
+    for f in clips["flat+noise block"]:
+        f[40:80, 50:120] = rng.integers(90, 170, size=(40, 70, 3))
+    for name, frames in clips.items():
+        proc, oproc = L.MagnificationProcessor(0), O.MagnificationProcessor()
+        for t, f in enumerate(frames):
+            produced, out = proc.process_image(f, cfg)
+            oprod, oout = oproc.process(f, ocfg)
+            assert produced == oprod, (name, t)
+            if produced:
+                d = u8_diff(out, oout)
+                assert int(d.max()) <= 3 and float((d == 0).mean()) >= 0.995, (name, t, int(d.max()), float((d == 0).mean()))
+                if name == "letterbox":
+                    assert (oout[:8] == 255).all() and (out[:8] == 255).all()      # the bars are white in both

@@ -110,6 +110,12 @@ def test_lab2bgr_device_function_matches_cv2(hc):
     hc.hc_lab_to_bgr(lab.ctypes.data_as(C.c_void_p), len(lab), got.ctypes.data_as(C.c_void_p))
     ref = cv2.cvtColor(lab[None], cv2.COLOR_Lab2BGR)[0]
     assert float(np.abs(got - ref).max()) < 2e-5
+    # non-finite L (Phase mode: 0/0 in flat regions): OpenCV's clip max(min(v,1),0) turns NaN into 1.0
+    odd = np.array([[np.nan, 0, 0], [np.nan, 40, -30], [np.inf, 0, 0], [-np.inf, 5, 5], [1e30, 0, 0], [-1e30, 0, 0]], np.float32)
+    odd = np.ascontiguousarray(np.tile(odd, (3, 1)))
+    got = np.empty_like(odd)
+    hc.hc_lab_to_bgr(odd.ctypes.data_as(C.c_void_p), len(odd), got.ctypes.data_as(C.c_void_p))
+    assert np.array_equal(got, cv2.cvtColor(odd[None], cv2.COLOR_Lab2BGR)[0])
 
 
 def test_u8_quantiser_and_ema_match_oracle_helpers(hc):
