@@ -732,7 +732,9 @@ def magnify_color(in8u: np.ndarray, p: MagnificationParams, levels: int, channel
         debug["output_f32"], debug["min"], debug["max"] = output, mn, mx
         debug["filtered"] = filtered
     with np.errstate(all="ignore"):
-        out8 = _f32_to_u8(output, 255.0 / (mx - mn), -mn * 255.0 / (mx - mn))  # :202-203
+        # C++ double arithmetic: a constant image gives 255/0 = inf and -min*255/0 = -inf or NaN, no exception
+        span = np.float64(mx) - np.float64(mn)
+        out8 = _f32_to_u8(output, float(np.float64(255.0) / span), float(np.float64(-mn) * 255.0 / span))  # :202-203
     return True, out8
 
 
