@@ -314,6 +314,9 @@ def run_ours(args, rank, world, local_rank):
     fps = world * lanes * args.steps / (ms * 1e-3)
 
     # ---- end to end through the host API (pinned frames in / out, copies inside the region) ----
+    # the pinned staging buffers are allocated (first touched) on the NUMA node of this rank's GPU
+    from lvm_b200.shard import bind_to_gpu_numa_node
+    prev_affinity, numa = bind_to_gpu_numa_node(local_rank)
     clip_p = torch.from_numpy(clip_h).pin_memory()
     depth = 3
     outs_p = [torch.empty((lanes, H, W, CH), dtype=torch.uint8).pin_memory() for _ in range(depth)]
@@ -339,6 +342,8 @@ def run_ours(args, rank, world, local_rank):
     clocks = sampler.stop() if rank == 0 else None
     e2e_fps = world * lanes * args.steps / e2e_s
     barrier()
+    if prev_affinity is not None:
+        os.sched_setaffinity(0, prev_affinity)   # the CPU baseline below uses every host core again
 
     # ---- per-kernel device time (roofline of the dominant kernel) -------------------------------
     roof = None
@@ -389,7 +394,7 @@ def run_ours(args, rank, world, local_rank):
                        "clip_frames": T,
                        "l2": f"inputs {T * frame_bytes / 1e6:.0f} MB + per-lane state cycle through > L2 (126 MB); no flush needed"},
             "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": frame_bytes,
-                    "d2h_bytes_per_step": frame_bytes, "pipeline_depth": depth},
+                    "d2h_bytes_per_step": frame_bytes, "pipeline_depth": depth, "numa": numa},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
         })
     if dist:

@@ -10,6 +10,37 @@ from typing import List, Optional
 from .capi import McParams
 
 
+def bind_to_gpu_numa_node(device_index: int):
+    """Pins the calling process to the CPUs of the NUMA node its GPU hangs off, so that the pinned frame buffers it
+    allocates next are local to that GPU's PCIe root (one process per GPU: without this, ranks on a two-socket box
+    stage half of their frames across the socket interconnect).  Returns (previous affinity, info dict) — restore with
+    os.sched_setaffinity(0, previous) — or (None, {...reason}) when the topology cannot be read.  Linux sysfs only;
+    never raises."""
+    import os
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(device_index)
+        bus = f"{getattr(pr, 'pci_domain_id', 0):04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None, {"numa_node": None, "reason": "single NUMA node / not reported"}
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        prev = os.sched_getaffinity(0)
+        cpus &= prev
+        if not cpus:
+            return None, {"numa_node": node, "reason": "no allowed CPU on that node"}
+        os.sched_setaffinity(0, cpus)
+        return prev, {"numa_node": node, "cpus": len(cpus), "pci": bus}
+    except Exception as e:   # noqa: BLE001 — topology is best effort
+        return None, {"numa_node": None, "reason": repr(e)[:80]}
+
+
 def shard_streams(total_streams: int, rank: int, world: int) -> List[int]:
     """Contiguous, balanced partition of stream ids 0..total-1 across ranks (weak scaling uses
     total = lanes_per_gpu * world so every rank gets exactly lanes_per_gpu)."""

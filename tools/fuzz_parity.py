@@ -5,6 +5,8 @@ modes, levels and parameters â€” with mid-stream parameter changes and resets â€
 
     MC_EMU=1 python tools/fuzz_parity.py --cases 200 --seed 0      # on the CUDA-on-CPU emulation (no GPU)
     python tools/fuzz_parity.py --cases 500                         # on a B200
+    MC_EMU=1 python tools/fuzz_parity.py --chain --cases 500        # the fused front of the chain (ROI / INTER_AREA /
+                                                                    # gray): original tap bit-exact, frame <= 1 LSB
 """
 import argparse
 import os
@@ -50,15 +52,58 @@ def make_frames(rng, w, h, c, n, kind):
     return frames
 
 
+def fuzz_chain(args):
+    import lvm_b200 as L
+    from oracle import livim_oracle as O, livim_ref
+    from common import make_cfgs
+    R = livim_ref.load()
+    assert R is not None, "the chain fuzz checks against the compiled reference (oracle/_ref)"
+    rng = np.random.default_rng(args.seed)
+    bad, t0 = 0, time.time()
+    for case in range(args.cases):
+        w, h, c = int(rng.integers(8, args.max_size + 40)), int(rng.integers(8, args.max_size + 40)), int(rng.choice([1, 3]))
+        down, gray, roi_on = int(rng.choice([1, 2, 3, 4, 5, 7, 8, 0, 9])), bool(rng.random() < 0.4), bool(rng.random() < 0.6)
+        roi = rng.uniform(-0.1, 1.1, size=4) if rng.random() < 0.3 else \
+            (rng.uniform(0, 0.6), rng.uniform(0, 0.6), rng.uniform(0.05, 1.0), rng.uniform(0.05, 1.0))
+        roi = [float(np.float32(v)) for v in roi]
+        cfg, ocfg = make_cfgs(O.MODE_LAPLACE, 20, 50.0, 0.4, 3.0, 20, int(rng.integers(1, 5)))
+        cfg.grayscale = ocfg.grayscale = gray
+        cfg.preprocess, ocfg.preprocess = L.PreprocessParams(down, roi_on, *roi), O.PreprocessParams(down, roi_on, *roi)
+        rcfg = livim_ref.to_ref_config(R, ocfg)
+        chain, rchain = L.ProcessingChainB200(0), R.Chain()
+        desc = f"chain case {case} seed {args.seed}: {w}x{h}x{c} down={down} gray={gray} roi_on={roi_on} roi={roi}"
+        try:
+            for t in range(3):
+                f = rng.integers(0, 256, size=(h, w, 3) if c == 3 else (h, w)).astype(np.uint8)
+                cur, orig = chain.run_chain_once(L.Frame(image=f, seq=t), cfg)
+                rcur, rorig, _, _, _ = rchain.process(f, rcfg)
+                if orig.image.shape != rorig.shape or not np.array_equal(orig.image, rorig):
+                    print("ORIGINAL TAP DIFFERS", desc, "frame", t)
+                    bad += 1
+                    break
+                if cur.image.shape != rcur.shape or int(np.abs(cur.image.astype(np.int32) - rcur.astype(np.int32)).max()) > 1:
+                    print("FRAME DIFFERS", desc, "frame", t)
+                    bad += 1
+                    break
+        except Exception as e:   # noqa: BLE001
+            print("EXCEPTION", desc, repr(e)[:200])
+            bad += 1
+    print(f"{args.cases} chain cases, {bad} outside tolerance, {time.time() - t0:.0f} s")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--cases", type=int, default=100)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--max-size", type=int, default=120)
+    ap.add_argument("--chain", action="store_true")
+    ap.add_argument("--options", action="store_true", help="also switch random A/B kernel options on (Laplace)")
     args = ap.parse_args()
     if os.environ.get("MC_EMU") == "1":
         import conftest
         conftest.use_emulated_library()
+    if args.chain:
+        return fuzz_chain(args)
     import lvm_b200 as L
     from oracle import livim_oracle as O, livim_ref
     from common import make_cfgs
@@ -87,13 +132,20 @@ def main():
         frames = make_frames(rng, w, h, c, n, kind)
         cfg, ocfg = make_cfgs(mode, *ui, fps)
         proc = L.MagnificationProcessor(0)
+        opts = []
+        if args.options:
+            opts = [k for k in ("prefetch_state", "egress_tma", "use_tail", "band_from_state", "faithful_level0", "use_tma")
+                    if rng.random() < 0.4]
+            for k in opts:
+                proc.set_option(k, 0 if k == "use_tma" else 1)
         if R is not None:
             ref, rcfg = R.Processor(), livim_ref.to_ref_config(R, ocfg)
         else:
             ref, rcfg = O.MagnificationProcessor(), ocfg
         change_at = int(rng.integers(2, n)) if rng.random() < 0.4 else -1
         reset_at = int(rng.integers(2, n)) if rng.random() < 0.15 else -1
-        desc = f"case {case} seed {args.seed}: mode {mode} {w}x{h}x{c} {kind} n={n} fps={fps} ui={ui} change@{change_at} reset@{reset_at}"
+        desc = (f"case {case} seed {args.seed}: mode {mode} {w}x{h}x{c} {kind} n={n} fps={fps} ui={ui} change@{change_at} "
+                f"reset@{reset_at} options={opts}")
         try:
             for t, f in enumerate(frames):
                 if t == change_at:   # non-structural change: same levels, new alpha / cutoffs / wavelength / chroma
