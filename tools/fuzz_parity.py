@@ -116,7 +116,7 @@ def main():
         w, h = int(rng.integers(6, args.max_size + 1)), int(rng.integers(6, args.max_size + 1))
         c = 3 if mode == O.MODE_PHASE or rng.random() < 0.7 else 1
         kind = str(rng.choice(kinds))
-        if mode == O.MODE_COLOR and kind == "flat":
+        if mode == O.MODE_COLOR and kind == "flat" and not os.environ.get("FUZZ_KEEP_COLOR_FLAT"):
             # a temporally constant window is degenerate in the reference itself: its temporal DFT is exactly zero for
             # some window lengths and rounding noise for others (OpenCV's per-length FFT kernels), and the min-max
             # normalisation stretches that noise to full range — not reproducible by any other FFT
@@ -146,11 +146,14 @@ def main():
         reset_at = int(rng.integers(2, n)) if rng.random() < 0.15 else -1
         desc = (f"case {case} seed {args.seed}: mode {mode} {w}x{h}x{c} {kind} n={n} fps={fps} ui={ui} change@{change_at} "
                 f"reset@{reset_at} options={opts}")
+        if os.environ.get("FUZZ_VERBOSE"):
+            print(desc, flush=True)
         try:
             for t, f in enumerate(frames):
                 if t == change_at:   # non-structural change: same levels, new alpha / cutoffs / wavelength / chroma
                     u2 = params()
                     ui2 = (u2[0], u2[1], u2[2], u2[3], u2[4], ui[5])
+                    desc += f" ui2={ui2}"
                     cfg, ocfg = make_cfgs(mode, *ui2, fps)
                     rcfg = livim_ref.to_ref_config(R, ocfg) if R is not None else ocfg
                 if t == reset_at:
