@@ -25,6 +25,8 @@ UNITS = ["mc_core.cu", "mc_laplace.cu", "mc_motion.cu", "mc_color.cu", "mc_riesz
 
 
 def lib_path(asan: bool = False) -> str:
+    if asan and os.environ.get("MC_EMU_UBSAN") == "1":
+        return os.path.join(HERE, "libmagcore_emu_ubsan.so")
     return os.path.join(HERE, "libmagcore_emu_asan.so" if asan else "libmagcore_emu.so")
 
 
@@ -95,11 +97,14 @@ def build(asan: bool = False, force: bool = False) -> str:
         [os.path.join(HERE, "emu_runtime.cpp"), __file__, os.path.join(ROOT, "include", "magcore_b200.h")]
     if not force and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in deps):
         return out
-    gen = GEN + ("_asan" if asan else "")
+    ubsan = asan and os.environ.get("MC_EMU_UBSAN") == "1"   # MC_EMU_ASAN=1 MC_EMU_UBSAN=1: UndefinedBehaviorSanitizer instead
+    gen = GEN + ("_ubsan" if ubsan else "_asan" if asan else "")
     os.makedirs(gen, exist_ok=True)
     flags = ["-std=c++17", "-O1", "-g", "-fPIC", "-ffp-contract=off", "-fno-strict-aliasing", "-D__CUDACC__", "-D__CUDA_ARCH__=1000",
              "-I", inc, "-I", CSRC, "-I", os.path.join(ROOT, "include"), "-Wno-unknown-pragmas", "-Wno-attributes"]
-    if asan:
+    if ubsan:
+        flags += ["-fsanitize=undefined", "-fno-sanitize-recover=undefined", "-fno-omit-frame-pointer"]
+    elif asan:
         flags += ["-fsanitize=address", "-fno-omit-frame-pointer"]
     jobs = []
     for u, path in zip(UNITS, srcs):
@@ -123,7 +128,7 @@ def build(asan: bool = False, force: bool = False) -> str:
         objs = list(ex.map(cc, jobs))
     lut_o = os.path.join(gen, "lab_lut_s16.o")
     subprocess.run(["ld", "-r", "-b", "binary", "-z", "noexecstack", "-o", lut_o, "lab_lut_s16.bin"], cwd=CSRC, check=True)
-    link = ["g++", "-shared", "-o", out, *objs, lut_o] + (["-fsanitize=address"] if asan else [])
+    link = ["g++", "-shared", "-o", out, *objs, lut_o] + (["-fsanitize=undefined"] if ubsan else ["-fsanitize=address"] if asan else [])
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout[-4000:])
