@@ -33,6 +33,7 @@ struct Fiber {
 struct Warp {
     unsigned gen = 0;
     unsigned buf[2][32];
+    unsigned stamp[2][32];   // generation + 1 in which the slot was written: a lane that has exited since still counts
 };
 
 ucontext_t g_sched;
@@ -85,6 +86,7 @@ void fiber_entry() {
 void run_block(unsigned n, const char* name) {
     const unsigned nwarps = (n + 31) / 32;
     g_warps.assign(nwarps, Warp{});
+    for (auto& w : g_warps) std::memset(w.stamp, 0, sizeof(w.stamp));
     for (unsigned t = 0; t < n; ++t) {
         Fiber& f = g_fibers[t];
         getcontext(&f.ctx);
@@ -95,10 +97,28 @@ void run_block(unsigned n, const char* name) {
         f.state = READY;
         f.tid = uint3{t % blockDim.x, (t / blockDim.x) % blockDim.y, t / (blockDim.x * blockDim.y)};
     }
+    // Poor man's racecheck: CUDA gives no order between the threads of a CTA except at barriers, so a kernel whose
+    // result depends on the order in which the emulation runs them has a shared-memory (or global) race.
+    // CUDA_EMU_ORDER=reverse | random runs the fibers in another order between synchronisation points.
+    static const int order_mode = [] {
+        const char* e = std::getenv("CUDA_EMU_ORDER");
+        return !e ? 0 : (std::string(e) == "reverse" ? 1 : (std::string(e) == "random" ? 2 : 0));
+    }();
+    static unsigned long long lcg = 0x9E3779B97F4A7C15ull;
+    static const char* only = std::getenv("CUDA_EMU_ORDER_KERNEL");   // restrict the permutation to kernels containing this
+    const int mode = (only && !std::strstr(name, only)) ? 0 : order_mode;
+    std::vector<unsigned> order(n);
+    for (unsigned t = 0; t < n; ++t) order[t] = mode == 1 ? n - 1 - t : t;
     unsigned done = 0;
     while (done < n) {
         bool progress = false;
-        for (unsigned t = 0; t < n; ++t) {
+        if (mode == 2)
+            for (unsigned i = n - 1; i > 0; --i) {
+                lcg = lcg * 6364136223846793005ull + 1442695040888963407ull;
+                std::swap(order[i], order[(unsigned)((lcg >> 33) % (i + 1))]);
+            }
+        for (unsigned oi = 0; oi < n; ++oi) {
+            const unsigned t = order[oi];
             Fiber& f = g_fibers[t];
             if (f.state != READY && f.state != SPIN) continue;
             const bool was_spin = f.state == SPIN;
@@ -184,6 +204,7 @@ unsigned shfl(unsigned bits, int arg, int mode, int width) {
     Warp& w = g_warps[t / 32];
     const unsigned mygen = w.gen;
     w.buf[mygen & 1][lane] = bits;
+    w.stamp[mygen & 1][lane] = mygen + 1;
     g_fibers[t].state = AT_WARP;
     yield_to_scheduler();
     Warp& w2 = g_warps[t / 32];
@@ -195,8 +216,9 @@ unsigned shfl(unsigned bits, int arg, int mode, int width) {
     case 2: src = (int)lane + arg; if (src > seg + width - 1) src = (int)lane; break;
     default: src = (int)lane ^ arg; if (src > seg + width - 1 || src < seg) src = (int)lane; break;
     }
-    const unsigned st = (t & ~31u) + (unsigned)src;
-    if (st >= g_fibers.size() || st >= blockDim.x * blockDim.y * blockDim.z || g_fibers[st].state == DONE) return bits;   // inactive source lane
+    // a source lane that did not take part in this shuffle (exited earlier, or beyond the block) yields the caller's own
+    // value; one that took part and has exited SINCE is still a valid source
+    if (w2.stamp[mygen & 1][src] != mygen + 1) return bits;
     return w2.buf[mygen & 1][src];
 }
 
