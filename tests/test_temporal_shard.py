@@ -37,20 +37,33 @@ def check(outs, ref):
     assert int(d.max()) <= 1 and float((d == 0).mean()) >= 0.999, (int(d.max()), float((d == 0).mean()))
 
 
-def run_in_process(cuts, n):
+def run_in_process(cuts, n, mode=O.MODE_LAPLACE, ui=(20, 50.0, 0.4, 3.0, 30, LEVELS), fps=30.0, size=(W, H), phase_tol=False):
     """all 'ranks' in this process, one after another, a dict as the transport"""
-    cfg, _ = make_cfgs(O.MODE_LAPLACE, 20, 50.0, 0.4, 3.0, 30, LEVELS)
-    frames = clip(n)
-    ref, _ = single_stream(frames, cfg)
+    cfg, _ = make_cfgs(mode, *ui, fps)
+    frames = [synth_frame(t, size[0], size[1], 3, fps=fps) for t in range(n)]
+    proc = L.MagnificationProcessor(0)
+    ref = [proc.process_image(f, cfg) for f in frames]
+    proc.close()
     bounds = [0] + list(cuts) + [n]
     world = len(bounds) - 1
+    need = shard.preroll_frames(cfg)
     mailbox, outs = {}, []
     for rank in range(world):
-        seg = frames[bounds[rank]:bounds[rank + 1]]
-        outs += shard.magnify_segment(seg, cfg, rank, world, lambda: L.MagnificationProcessor(0),
+        lo, hi = bounds[rank], bounds[rank + 1]
+        outs += shard.magnify_segment(frames[lo:hi], cfg, rank, world, lambda: L.MagnificationProcessor(0),
                                       send=lambda flat, dst: mailbox.__setitem__(dst, flat.copy()),
-                                      recv=lambda m, src, r=rank: mailbox.pop(r))
-    check(outs, ref)
+                                      recv=lambda m, src, r=rank: mailbox.pop(r),
+                                      preroll=frames[max(0, lo - need):lo] if rank else ())
+    assert len(outs) == n
+    for t, (o, (produced, r)) in enumerate(zip(outs, ref)):
+        if not produced:                       # passthrough frames of the single stream (warm-up) come back as the input
+            assert o is frames[t] or np.array_equal(o, frames[t]), t
+            continue
+        d = u8_diff(o, r)
+        if phase_tol:
+            assert int(d.max()) <= 3 and float((d == 0).mean()) >= 0.995, (t, int(d.max()), float((d == 0).mean()))
+        else:
+            assert int(d.max()) <= 1 and float((d == 0).mean()) >= 0.999, (t, int(d.max()), float((d == 0).mean()))
 
 
 @pytest.fixture()
@@ -66,6 +79,20 @@ def emu():
 @pytest.mark.parametrize("cuts,n", [((5,), 9), ((3, 4, 8), 10), ((1,), 3)])
 def test_state_carry_in_process_on_emulation(emu, cuts, n):
     run_in_process(cuts, n)
+
+
+@pytest.mark.emu
+def test_color_segments_with_window_preroll_on_emulation(emu):
+    """Color has a finite memory (the rolling window): pre-rolling window-1 frames reproduces the single stream; a cut
+    inside the clip's own warm-up (fewer frames available than the window) and one in steady state."""
+    run_in_process((6, 26), 34, mode=O.MODE_COLOR, ui=(100, 0.0, 0.8, 1.2, 0, 2), fps=8.0, size=(64, 48))
+
+
+@pytest.mark.emu
+def test_phase_segments_with_register_carry_on_emulation(emu):
+    """Phase: two pre-roll frames (the reference's first frame leaves the prior pyramid without its Riesz pair) + the 3x3
+    linear carry of (phase, r0, r1) per Butterworth filter and component; cuts at frame 1 (one pre-roll frame exists), 4, 7."""
+    run_in_process((1, 4, 7), 11, mode=O.MODE_PHASE, ui=(50, 50.0, 0.4, 3.0, 0, 3), size=(96, 64), phase_tol=True)
 
 
 @pytest.mark.emu
@@ -152,7 +179,14 @@ def test_state_carry_on_gpu(cuts, n):
     run_in_process(cuts, n)
 
 
-def test_other_modes_are_rejected():
-    cfg, _ = make_cfgs(O.MODE_COLOR, 100, 0.0, 0.8, 1.2, 0, 2)
-    with pytest.raises(NotImplementedError):
-        shard.magnify_segment([np.zeros((8, 8, 3), np.uint8)], cfg, 0, 1, lambda: None, None, None)
+@pytest.mark.gpu
+def test_color_and_phase_segments_on_gpu():
+    run_in_process((6, 26), 34, mode=O.MODE_COLOR, ui=(100, 0.0, 0.8, 1.2, 0, 2), fps=8.0, size=(160, 120))
+    run_in_process((1, 4, 7), 11, mode=O.MODE_PHASE, ui=(50, 50.0, 0.4, 3.0, 0, 3), size=(160, 120), phase_tol=True)
+
+
+def test_preroll_requirements():
+    for mode, ui, fps, want in ((O.MODE_LAPLACE, (20, 50.0, 0.4, 3.0, 0, 4), 30.0, 0), (O.MODE_PHASE, (50, 50.0, 0.4, 3.0, 0, 4), 30.0, 2),
+                                (O.MODE_COLOR, (100, 0.0, 0.8, 1.2, 0, 3), 30.0, 63), (O.MODE_COLOR, (100, 0.0, 0.8, 1.2, 0, 3), 8.0, 15)):
+        cfg, _ = make_cfgs(mode, *ui, fps)
+        assert shard.preroll_frames(cfg) == want
