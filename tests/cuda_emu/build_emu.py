@@ -4,7 +4,7 @@ The product's own sources (live-video-magnification_b200/csrc/*.cu, mc_tables.cp
 CUDA-on-CPU emulation in tests/cuda_emu/include, so the kernels' *logic* (indexing, borders, tile staging, the
 arithmetic of the device code paths) can be exercised by the parity tests in a container without a GPU, under
 AddressSanitizer if wanted.  The only source transformation is the launch syntax: `k<<<cfg>>>(args)` becomes
-`cuda_emu::Launcher(cfg).run("k", [&]() { k(args); })`.  The result exports the same C ABI as libmagcore_b200.so
+`cuda_emu::Launcher(cfg).run("k", (k), args)`.  The result exports the same C ABI as libmagcore_b200.so
 but is never loaded by the product (tests/conftest.py points lvm_b200.capi at it only when MC_EMU=1).
 
     python tests/cuda_emu/build_emu.py [--asan]
@@ -84,7 +84,7 @@ def rewrite_launches(src: str) -> str:
         args = src[lp + 1:rp]
         name = " ".join(kernel.split())   # keeps the template arguments: visible with CUDA_EMU_TRACE=1
         out.append(src[pos:b])
-        out.append(f'cuda_emu::Launcher({cfg}).run("{name}", [&]() {{ {kernel}({args}); }})')
+        out.append(f'cuda_emu::Launcher({cfg}).run("{name}", ({kernel}){", " if args.strip() else ""}{args})')
         pos = rp + 1
 
 

@@ -6,7 +6,9 @@
 #include <ucontext.h>
 
 #include <chrono>
+#include <deque>
 #include <map>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -300,10 +302,74 @@ static CUresult emu_cuTensorMapEncodeTiled(CUtensorMap* tm, CUtensorMapDataType 
     return CUDA_SUCCESS;
 }
 
+// ---- streams and events --------------------------------------------------------------------------------------------
+// Default: every operation runs at the call (one legal schedule).  CUDA_EMU_ASYNC=1: operations on a stream are queued
+// and only executed when the host synchronises (stream / event / device sync, cudaFree), in a pseudo-random order
+// (CUDA_EMU_SEED) that respects nothing but stream order and event waits — so a missing cudaStreamWaitEvent, a buffer
+// reused before its consumer ran, or a host buffer touched while an async copy is pending shows up as a wrong result.
+// As in CUDA, synchronous copies on the null stream do NOT wait for the (non-blocking) user streams.
+namespace cuda_emu {
+namespace {
+struct EmuEvent {
+    unsigned long long recorded = 0, completed = 0;   // sequence numbers of cudaEventRecord calls / executions
+    std::chrono::steady_clock::time_point t;
+};
+struct Op {
+    std::function<void()> work;       // kind 0
+    int kind = 0;                     // 0 work, 1 record, 2 wait
+    EmuEvent* ev = nullptr;
+    unsigned long long seq = 0;
+};
+std::map<void*, std::deque<Op>> g_queues;
+unsigned long long g_rng = 0;
+bool async_mode() {
+    static const bool on = [] {
+        const char* e = std::getenv("CUDA_EMU_ASYNC");
+        const char* sd = std::getenv("CUDA_EMU_SEED");
+        g_rng = 0x2545F4914F6CDD1Dull ^ (sd ? std::strtoull(sd, nullptr, 10) * 0x9E3779B97F4A7C15ull : 0);
+        return e && e[0] == '1';
+    }();
+    return on;
+}
+bool ready(const Op& op) { return op.kind != 2 || op.ev->completed >= op.seq; }
+void execute(Op& op) {
+    if (op.kind == 0) op.work();
+    else if (op.kind == 1) { op.ev->completed = std::max(op.ev->completed, op.seq); op.ev->t = std::chrono::steady_clock::now(); }
+}
+// runs queued operations in a random legal order until done() holds
+template <typename Pred> void drain_until(Pred done) {
+    while (!done()) {
+        std::vector<std::deque<Op>*> cand;
+        for (auto& kv : g_queues)
+            if (!kv.second.empty() && ready(kv.second.front())) cand.push_back(&kv.second);
+        if (cand.empty()) {
+            std::fprintf(stderr, "cuda_emu: stream deadlock — a wait on an event that is never recorded, or a synchronise on work that cannot run\n");
+            std::abort();
+        }
+        g_rng = g_rng * 6364136223846793005ull + 1442695040888963407ull;
+        std::deque<Op>* q = cand[(size_t)((g_rng >> 33) % cand.size())];
+        Op op = std::move(q->front());
+        q->pop_front();
+        execute(op);
+    }
+}
+void drain_all() {
+    drain_until([] { for (auto& kv : g_queues) if (!kv.second.empty()) return false; return true; });
+}
+}  // namespace
+
+void enqueue(void* stream, std::function<void()> work) {
+    if (!async_mode() || stream == nullptr) { work(); return; }
+    Op op;
+    op.work = std::move(work);
+    g_queues[stream].push_back(std::move(op));
+}
+}  // namespace cuda_emu
+
 // ---- runtime API -----------------------------------------------------------------------------------------------
 namespace {
 std::map<const void*, std::pair<size_t, int>> g_allocs;   // ptr -> (bytes, 1 device / 2 pinned host / 3 registered)
-struct EmuEvent { std::chrono::steady_clock::time_point t; };
+using cuda_emu::EmuEvent;
 }
 
 const char* cudaGetErrorString(cudaError_t e) {
@@ -328,7 +394,7 @@ cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int d) {
     p->totalGlobalMem = 8ull << 30; p->sharedMemPerBlock = 48 << 10; p->sharedMemPerBlockOptin = 227 << 10; p->l2CacheSize = 126 << 20;
     return cudaSuccess;
 }
-cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
+cudaError_t cudaDeviceSynchronize() { cuda_emu::drain_all(); return cudaSuccess; }
 static cudaError_t emu_alloc(void** p, size_t n, int kind) {
     void* q = std::aligned_alloc(256, (n + 255) / 256 * 256 + 256);
     if (!q) return cudaErrorMemoryAllocation;
@@ -338,7 +404,11 @@ static cudaError_t emu_alloc(void** p, size_t n, int kind) {
     return cudaSuccess;
 }
 cudaError_t cudaMalloc(void** p, size_t n) { return emu_alloc(p, n, 1); }
-cudaError_t cudaFree(void* p) { if (p) { g_allocs.erase(p); std::free(p); } return cudaSuccess; }
+cudaError_t cudaFree(void* p) {
+    cuda_emu::drain_all();   // cudaFree synchronises the device
+    if (p) { g_allocs.erase(p); std::free(p); }
+    return cudaSuccess;
+}
 cudaError_t cudaHostAlloc(void** p, size_t n, unsigned) { return emu_alloc(p, n, 2); }
 cudaError_t cudaMallocHost(void** p, size_t n) { return emu_alloc(p, n, 2); }
 cudaError_t cudaFreeHost(void* p) { return cudaFree(p); }
@@ -356,28 +426,96 @@ cudaError_t cudaPointerGetAttributes(cudaPointerAttributes* a, const void* p) {
     return cudaSuccess;
 }
 cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { if (n) std::memmove(d, s, n); return cudaSuccess; }
-cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind k, cudaStream_t) { return cudaMemcpy(d, s, n, k); }
+// what kind of memory a pointer is: 1 device, 2 / 3 pinned host (allocated / registered), 0 pageable host
+static int mem_kind(const void* p) {
+    auto it = g_allocs.upper_bound(p);
+    if (it == g_allocs.begin()) return 0;
+    --it;
+    return static_cast<const char*>(p) < static_cast<const char*>(it->first) + it->second.first ? it->second.second : 0;
+}
+// Asynchronous copies involving PAGEABLE host memory are not asynchronous in CUDA: a pageable source is staged before the
+// call returns (so the caller may reuse or free it), and a copy into pageable memory returns only once it has completed.
+cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t st) {
+    if (!n) return cudaSuccess;
+    if (cuda_emu::async_mode() && st) {
+        if (mem_kind(d) == 0) {                       // into pageable memory: synchronous with respect to the stream
+            cudaStreamSynchronize(st);
+            std::memmove(d, s, n);
+            return cudaSuccess;
+        }
+        if (mem_kind(s) == 0) {                       // from pageable memory: staged now
+            auto staged = std::make_shared<std::vector<unsigned char>>(static_cast<const unsigned char*>(s),
+                                                                       static_cast<const unsigned char*>(s) + n);
+            cuda_emu::enqueue(st, [=]() { std::memcpy(d, staged->data(), n); });
+            return cudaSuccess;
+        }
+    }
+    cuda_emu::enqueue(st, [=]() { std::memmove(d, s, n); });
+    return cudaSuccess;
+}
 cudaError_t cudaMemcpy2D(void* d, size_t dp, const void* s, size_t sp, size_t w, size_t h, cudaMemcpyKind) {
     if (w > dp || w > sp) return cudaErrorInvalidValue;
     for (size_t y = 0; y < h; ++y) std::memmove(static_cast<char*>(d) + y * dp, static_cast<const char*>(s) + y * sp, w);
     return cudaSuccess;
 }
-cudaError_t cudaMemcpy2DAsync(void* d, size_t dp, const void* s, size_t sp, size_t w, size_t h, cudaMemcpyKind k, cudaStream_t) {
-    return cudaMemcpy2D(d, dp, s, sp, w, h, k);
+cudaError_t cudaMemcpy2DAsync(void* d, size_t dp, const void* s, size_t sp, size_t w, size_t h, cudaMemcpyKind k, cudaStream_t st) {
+    if (w > dp || w > sp) return cudaErrorInvalidValue;
+    if (cuda_emu::async_mode() && st && (mem_kind(d) == 0 || mem_kind(s) == 0)) {   // pageable side: see cudaMemcpyAsync
+        cudaStreamSynchronize(st);
+        return cudaMemcpy2D(d, dp, s, sp, w, h, k);
+    }
+    cuda_emu::enqueue(st, [=]() { cudaMemcpy2D(d, dp, s, sp, w, h, k); });
+    return cudaSuccess;
 }
 cudaError_t cudaMemset(void* d, int v, size_t n) { if (n) std::memset(d, v, n); return cudaSuccess; }
-cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) { return cudaMemset(d, v, n); }
+cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t st) {
+    cuda_emu::enqueue(st, [=]() { if (n) std::memset(d, v, n); });
+    return cudaSuccess;
+}
 cudaError_t cudaStreamCreate(cudaStream_t* s) { *s = reinterpret_cast<cudaStream_t>(new int(0)); return cudaSuccess; }
 cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { return cudaStreamCreate(s); }
-cudaError_t cudaStreamDestroy(cudaStream_t s) { delete reinterpret_cast<int*>(s); return cudaSuccess; }
-cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
-cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
+cudaError_t cudaStreamSynchronize(cudaStream_t s) {
+    if (cuda_emu::async_mode() && s) cuda_emu::drain_until([s] { return cuda_emu::g_queues[s].empty(); });
+    return cudaSuccess;
+}
+cudaError_t cudaStreamDestroy(cudaStream_t s) {
+    cudaStreamSynchronize(s);
+    cuda_emu::g_queues.erase(s);
+    delete reinterpret_cast<int*>(s);
+    return cudaSuccess;
+}
+cudaError_t cudaStreamWaitEvent(cudaStream_t s, cudaEvent_t e, unsigned) {
+    auto* ev = reinterpret_cast<EmuEvent*>(e);
+    if (!cuda_emu::async_mode() || !s || ev->recorded == 0) return cudaSuccess;   // never recorded: no-op, as in CUDA
+    cuda_emu::Op op;
+    op.kind = 2; op.ev = ev; op.seq = ev->recorded;                               // the latest record before this call
+    cuda_emu::g_queues[s].push_back(std::move(op));
+    return cudaSuccess;
+}
 cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = reinterpret_cast<cudaEvent_t>(new EmuEvent{}); return cudaSuccess; }
 cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { return cudaEventCreate(e); }
-cudaError_t cudaEventDestroy(cudaEvent_t e) { delete reinterpret_cast<EmuEvent*>(e); return cudaSuccess; }
-cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) { reinterpret_cast<EmuEvent*>(e)->t = std::chrono::steady_clock::now(); return cudaSuccess; }
-cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+cudaError_t cudaEventDestroy(cudaEvent_t e) {
+    if (cuda_emu::async_mode()) cuda_emu::drain_all();   // pending operations may still refer to it
+    delete reinterpret_cast<EmuEvent*>(e);
+    return cudaSuccess;
+}
+cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t s) {
+    auto* ev = reinterpret_cast<EmuEvent*>(e);
+    const unsigned long long seq = ++ev->recorded;
+    if (!cuda_emu::async_mode() || !s) { ev->completed = seq; ev->t = std::chrono::steady_clock::now(); return cudaSuccess; }
+    cuda_emu::Op op;
+    op.kind = 1; op.ev = ev; op.seq = seq;
+    cuda_emu::g_queues[s].push_back(std::move(op));
+    return cudaSuccess;
+}
+cudaError_t cudaEventSynchronize(cudaEvent_t e) {
+    auto* ev = reinterpret_cast<EmuEvent*>(e);
+    if (cuda_emu::async_mode()) cuda_emu::drain_until([ev] { return ev->completed >= ev->recorded; });
+    return cudaSuccess;
+}
 cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) {
+    cudaEventSynchronize(a);
+    cudaEventSynchronize(b);
     *ms = std::chrono::duration<float, std::milli>(reinterpret_cast<EmuEvent*>(b)->t - reinterpret_cast<EmuEvent*>(a)->t).count();
     return cudaSuccess;
 }
@@ -394,25 +532,42 @@ cudaError_t cudaGetDriverEntryPoint(const char* symbol, void** fn, unsigned long
 
 // ---- cuFFT stand-in ------------------------------------------------------------------------------------------------
 namespace {
-struct Plan { int n, istride, idist, ostride, odist, batch; cufftType type; bool live; };
+struct Plan { int n, istride, idist, ostride, odist, batch; cufftType type; bool live; cudaStream_t stream; };
 std::vector<Plan> g_plans(1);   // handle 0 is "no plan"
 }
 cufftResult cufftPlanMany(cufftHandle* plan, int rank, int* n, int*, int istride, int idist, int*, int ostride, int odist,
                           cufftType type, int batch) {
     if (rank != 1 || n[0] < 1 || batch < 1 || (type != CUFFT_R2C && type != CUFFT_C2R)) return CUFFT_INVALID_VALUE;
-    g_plans.push_back(Plan{n[0], istride, idist, ostride, odist, batch, type, true});
+    g_plans.push_back(Plan{n[0], istride, idist, ostride, odist, batch, type, true, nullptr});
     *plan = (cufftHandle)g_plans.size() - 1;
     return CUFFT_SUCCESS;
 }
-cufftResult cufftSetStream(cufftHandle, cudaStream_t) { return CUFFT_SUCCESS; }
+cufftResult cufftSetStream(cufftHandle p, cudaStream_t s) {
+    if (p <= 0 || (size_t)p >= g_plans.size()) return CUFFT_INVALID_PLAN;
+    g_plans[(size_t)p].stream = s;
+    return CUFFT_SUCCESS;
+}
 cufftResult cufftDestroy(cufftHandle p) {
     if (p <= 0 || (size_t)p >= g_plans.size()) return CUFFT_INVALID_PLAN;
+    if (cuda_emu::async_mode()) cuda_emu::drain_all();
     g_plans[(size_t)p].live = false;
     return CUFFT_SUCCESS;
 }
+static cufftResult exec_r2c(Plan p, cufftReal* in, cufftComplex* out);
+static cufftResult exec_c2r(Plan p, cufftComplex* in, cufftReal* out);
 cufftResult cufftExecR2C(cufftHandle h, cufftReal* in, cufftComplex* out) {
     if (h <= 0 || (size_t)h >= g_plans.size() || !g_plans[(size_t)h].live || g_plans[(size_t)h].type != CUFFT_R2C) return CUFFT_INVALID_PLAN;
-    const Plan& p = g_plans[(size_t)h];
+    const Plan p = g_plans[(size_t)h];
+    cuda_emu::enqueue(p.stream, [=]() { exec_r2c(p, in, out); });
+    return CUFFT_SUCCESS;
+}
+cufftResult cufftExecC2R(cufftHandle h, cufftComplex* in, cufftReal* out) {
+    if (h <= 0 || (size_t)h >= g_plans.size() || !g_plans[(size_t)h].live || g_plans[(size_t)h].type != CUFFT_C2R) return CUFFT_INVALID_PLAN;
+    const Plan p = g_plans[(size_t)h];
+    cuda_emu::enqueue(p.stream, [=]() { exec_c2r(p, in, out); });
+    return CUFFT_SUCCESS;
+}
+static cufftResult exec_r2c(Plan p, cufftReal* in, cufftComplex* out) {
     const int n = p.n;
     std::vector<double> cs((size_t)n), sn((size_t)n), x((size_t)n);
     for (int j = 0; j < n; ++j) { cs[(size_t)j] = std::cos(2.0 * M_PI * j / n); sn[(size_t)j] = std::sin(2.0 * M_PI * j / n); }
@@ -426,9 +581,7 @@ cufftResult cufftExecR2C(cufftHandle h, cufftReal* in, cufftComplex* out) {
     }
     return CUFFT_SUCCESS;
 }
-cufftResult cufftExecC2R(cufftHandle h, cufftComplex* in, cufftReal* out) {
-    if (h <= 0 || (size_t)h >= g_plans.size() || !g_plans[(size_t)h].live || g_plans[(size_t)h].type != CUFFT_C2R) return CUFFT_INVALID_PLAN;
-    const Plan& p = g_plans[(size_t)h];
+static cufftResult exec_c2r(Plan p, cufftComplex* in, cufftReal* out) {
     const int n = p.n;
     std::vector<double> cs((size_t)n), sn((size_t)n), re((size_t)n / 2 + 1), im((size_t)n / 2 + 1);
     for (int j = 0; j < n; ++j) { cs[(size_t)j] = std::cos(2.0 * M_PI * j / n); sn[(size_t)j] = std::sin(2.0 * M_PI * j / n); }

@@ -18,6 +18,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <tuple>
+#include <utility>
 
 #define MC_CUDA_EMU 1
 
@@ -80,13 +82,22 @@ void* dyn_smem();    // the launch's dynamic shared memory (`extern __shared__`)
 typedef struct CUstream_st* cudaStream_t;
 namespace cuda_emu {
 // `k<<<grid, block, smem, stream>>>(args)` is rewritten by build_emu.py into
-// `cuda_emu::Launcher(grid, block, smem, stream).run("k", [&]() { k(args); })`
+// `cuda_emu::Launcher(grid, block, smem, stream).run("k", (k), args)`.  The arguments are copied at the launch, as
+// CUDA does; the work itself runs at once, or — with CUDA_EMU_ASYNC=1 — is queued on its stream and executed later in
+// a random order that only respects stream order and event dependencies (see enqueue below).
+void enqueue(void* stream, std::function<void()> work);
 struct Launcher {
     dim3 grid, block;
     size_t smem;
     void* stream;
     Launcher(dim3 g, dim3 b, size_t sm = 0, cudaStream_t s = nullptr) : grid(g), block(b), smem(sm), stream(s) {}
-    template <typename F> void run(const char* name, F&& f) { launch(grid, block, smem, stream, name, std::function<void()>(f)); }
+    template <typename K, typename... A> void run(const char* name, K kernel, A&&... args) {
+        auto packed = std::make_tuple(std::decay_t<A>(std::forward<A>(args))...);
+        const dim3 g = grid, b = block;
+        const size_t sm = smem;
+        void* st = stream;
+        enqueue(st, [=]() { launch(g, b, sm, st, name, [&]() { std::apply(kernel, packed); }); });
+    }
 };
 }  // namespace cuda_emu
 
