@@ -38,10 +38,11 @@ MC_HD float u8_to_unit(uint8_t v) { return (float)v * 0.003921568859368563f; }
 
 // f32 -> u8 as Mat::convertTo(CV_8U, 255, 1/255) does it (MagnifyCore.hpp:153):
 // saturate(round_half_even(fma(x, 255, (float)(1/255)))).
+// OpenCV rounds with cvtps2dq: NaN and anything outside the int32 range become INT_MIN and then saturate to 0.
 MC_HD uint8_t unit_to_u8(float x) {
     float v = fmaf(x, 255.0f, 0.003921568859368563f);
     v = rintf(v);
-    if (!(v > 0.0f)) return 0;   // also NaN -> 0
+    if (!(v > 0.0f) || v >= 2147483648.0f) return 0;   // NaN, negatives, +inf / out of int range -> 0
     if (v > 255.0f) return 255;
     return (uint8_t)(int)v;
 }
@@ -61,7 +62,7 @@ MC_HD uint8_t unit01_to_u8(float x) {
 // generic convertTo(CV_8U, alpha, beta) used by Color egress (MagnifyCore.hpp:202-203)
 MC_HD uint8_t scaled_to_u8(float x, float a, float b) {
     float v = rintf(fmaf(x, a, b));
-    if (!(v > 0.0f)) return 0;
+    if (!(v > 0.0f) || v >= 2147483648.0f) return 0;   // as unit_to_u8: cvtps2dq semantics
     if (v > 255.0f) return 255;
     return (uint8_t)(int)v;
 }

@@ -150,12 +150,15 @@ def _u8_to_f32_scaled(img8: np.ndarray, alpha: float) -> np.ndarray:
 
 
 def _f32_to_u8(img: np.ndarray, alpha: float, beta: float) -> np.ndarray:
-    """Mat::convertTo(CV_8U, alpha, beta) on CV_32F: saturate(round_half_even(fma(x, (float)a, (float)b)))."""
+    """Mat::convertTo(CV_8U, alpha, beta) on CV_32F: saturate(round_half_even(fma(x, (float)a, (float)b))).  The rounding
+    is cvtps2dq: NaN and values outside the int32 range become INT_MIN, which then saturates to 0 (so +inf -> 0)."""
     a, b = float(F32(alpha)), float(F32(beta))
-    v = (img.astype(np.float64) * a + b).astype(F32)  # one rounding == fmaf
-    v = np.rint(v.astype(np.float64))
-    v = np.where(np.isnan(v), 0.0, v)
-    return np.clip(v, 0, 255).astype(np.uint8)
+    with np.errstate(all="ignore"):
+        v = (img.astype(np.float64) * a + b).astype(F32)  # one rounding == fmaf
+        r = np.rint(v.astype(np.float64))
+    bad = ~np.isfinite(r) | (r >= 2147483648.0) | (r < -2147483648.0)
+    r = np.where(bad, -2147483648.0, r)
+    return np.clip(r, 0, 255).astype(np.uint8)
 
 
 def _scale(m: np.ndarray, s: float) -> np.ndarray:

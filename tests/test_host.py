@@ -126,8 +126,11 @@ def test_u8_quantiser_and_ema_match_oracle_helpers(hc):
     hc.hc_unit_to_u8(x.ctypes.data_as(C.c_void_p), len(x), got.ctypes.data_as(C.c_void_p))
     with np.errstate(all="ignore"):
         ref = O._f32_to_u8(x, 255.0, 1.0 / 255.0)
-    ok = np.isfinite(x)
-    assert np.array_equal(got[ok], ref[ok])
+    assert np.array_equal(got, ref)          # non-finite and huge inputs included (NaN, +-inf -> 0: cvtps2dq semantics)
+    huge = np.array([1e7, 8.0e6, 3e9, -3e9, 2147483648.0 / 255.0 + 1.0], np.float32)
+    got_h = np.empty(len(huge), np.uint8)
+    hc.hc_unit_to_u8(huge.ctypes.data_as(C.c_void_p), len(huge), got_h.ctypes.data_as(C.c_void_p))
+    assert np.array_equal(got_h, O._f32_to_u8(huge, 255.0, 1.0 / 255.0)) and got_h.tolist() == [0, 255, 0, 0, 0]
     s = rng.normal(0, 30, 100000).astype(np.float32)
     v = rng.normal(0, 30, 100000).astype(np.float32)
     out = np.empty_like(s)
