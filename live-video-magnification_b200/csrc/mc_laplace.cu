@@ -988,22 +988,28 @@ inline unsigned cdiv(int a, int b) { return (unsigned)((a + b - 1) / b); }
 
 }  // namespace
 
-// Encodes a 3-D tiled tensor map {w, h, planes} over pitched f32 planes with the level kernel's box.
-// cuTensorMapEncodeTiled is resolved through the runtime so the library needs no link-time libcuda.
-bool make_level_tensor_map(void* out_map, const float* base, const Level& l, int planes, bool state_tile) {
-    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-    static EncodeFn encode = nullptr;
-    if (!encode) {
-        void* fn = nullptr;
+// cuTensorMapEncodeTiled, resolved through the runtime so the library needs no link-time libcuda; thread-safe
+// (several handles may be created from different threads: live chain + exporter)
+typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TensorMapEncodeFn tensor_map_encoder() {
+    static const TensorMapEncodeFn fn = [] {
+        void* p = nullptr;
         cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess || !p) {
             cudaGetLastError();
-            return false;
+            p = nullptr;
         }
-        encode = reinterpret_cast<EncodeFn>(fn);
-    }
+        return reinterpret_cast<TensorMapEncodeFn>(p);
+    }();
+    return fn;
+}
+
+// Encodes a 3-D tiled tensor map {w, h, planes} over pitched f32 planes with the level kernel's box.
+bool make_level_tensor_map(void* out_map, const float* base, const Level& l, int planes, bool state_tile) {
+    const TensorMapEncodeFn encode = tensor_map_encoder();
+    if (!encode) return false;
     const cuuint64_t dims[3] = {(cuuint64_t)l.w, (cuuint64_t)l.h, (cuuint64_t)planes};
     const cuuint64_t strides[2] = {(cuuint64_t)l.pitch * sizeof(float), (cuuint64_t)l.plane * sizeof(float)};
     // input window (72 x 39, origin x0-4, y0-4) or state tile (64 x 32, origin x0, y0)
@@ -1080,20 +1086,13 @@ cudaError_t launch_collapse(const Level& lf, const Level& lc, const BandSrc& fin
 // {w, h, planes} map over pitched planes of `elem_bytes`-wide elements (4: f32, 2: 16-bit) with an arbitrary box
 bool make_plane_tensor_map(void* out_map, const void* base, int elem_bytes, int w, int h, int planes, size_t row_bytes,
                            size_t plane_bytes, int box_w, int box_h, int box_d) {
-    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-    void* fn = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
-        cudaGetLastError();
-        return false;
-    }
+    const TensorMapEncodeFn fn = tensor_map_encoder();
+    if (!fn) return false;
     const cuuint64_t dims[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)planes};
     const cuuint64_t strides[2] = {(cuuint64_t)row_bytes, (cuuint64_t)plane_bytes};
     const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)box_d};
     const cuuint32_t estr[3] = {1u, 1u, 1u};
-    return reinterpret_cast<EncodeFn>(fn)(reinterpret_cast<CUtensorMap*>(out_map),
+    return fn(reinterpret_cast<CUtensorMap*>(out_map),
                                           elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT16, 3,
                                           const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -1144,12 +1143,11 @@ cudaError_t launch_tail(TailArgs& a, int planes, cudaStream_t s) {
         off += (a.lv[l].w * a.lv[l].h + 3) / 4 * 4;
     }
     const size_t bytes = (size_t)off * sizeof(float);
-    static size_t configured = 0;
-    if (bytes > configured) {   // opt in to > 48 KB of dynamic shared memory (once per size increase)
-        cudaError_t e = cudaFuncSetAttribute(k_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-        if (e != cudaSuccess) return e;
-        configured = bytes;
-    }
+    // opt in to > 48 KB of dynamic shared memory: a per-device function attribute, cheap to set, so it is set on every
+    // launch (always to the full budget: handles on several devices / threads agree on the value)
+    if (bytes > kTailSmemBudget) return cudaErrorInvalidValue;
+    const cudaError_t e = cudaFuncSetAttribute(k_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTailSmemBudget);
+    if (e != cudaSuccess) return e;
     k_tail<<<planes, 1024, bytes, s>>>(a);
     return cudaGetLastError();
 }
