@@ -129,6 +129,10 @@ def main():
             return (int(rng.choice([0, 5, 20, 50, 150])), float(rng.choice([0.0, 10.0, 50.0, 90.0, 100.0])), lo,
                     lo + float(rng.choice([0.0, 0.4, 2.5, 20.0])), int(rng.choice([0, 30, 100])), int(rng.integers(1, 9)))
         ui = params()
+        if mode == O.MODE_PHASE and ui[3] > fps / 2:
+            # beyond Nyquist the reference's Butterworth design has poles outside the unit circle (the UI clamps to Nyquist):
+            # the registers explode within a few frames and any rounding difference with them
+            ui = ui[:3] + (fps / 2,) + ui[4:]
         frames = make_frames(rng, w, h, c, n, kind)
         cfg, ocfg = make_cfgs(mode, *ui, fps)
         proc = L.MagnificationProcessor(0)
