@@ -165,8 +165,9 @@ void* mc_stream(mc_handle* h);
  *        level and direction (results within float rounding of the per-level kernels; for A/B measurements)
  *   "egress_tma" (default 0; needs use_tma; 3-channel frames): the egress kernel requests its Lab16 tile, its level-1
  *        band window and its level-2 window as TMA bulk copies at kernel entry (same results; for A/B measurements)
- *   "analysis_only" (default 0): Laplace only — frames after the first update the temporal state but skip
- *        synthesis and egress and report *produced = 0; the cheap first pass of temporal sharding
+ *   "analysis_only" (default 0): Laplace and Phase — frames after the first update the temporal state (EMA planes;
+ *        Riesz pyramids, phase accumulators and Butterworth registers) but skip synthesis and egress and report
+ *        *produced = 0; the cheap first pass of temporal sharding
  *   "band_from_state" (default 0): Laplace synthesis rebuilds each amplified band gain*(hi-lo) from the two
  *        state planes instead of reading a band plane stored by the level kernel (same results; takes 4 B/px off
  *        the level kernel's interface and adds them to the collapse / egress kernels; kept for A/B measurements) */

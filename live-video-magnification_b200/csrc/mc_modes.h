@@ -43,7 +43,7 @@ struct ModeCtx {
                             // until measured on the B200)
     bool band_from_state;   // synthesis rebuilds gain*(hi-lo) from the state planes instead of reading a stored band
                             // (option "band_from_state", default off: measured no faster on B200)
-    bool analysis_only;     // Laplace: update the temporal state but skip synthesis + egress (*produced = 0); used by the
+    bool analysis_only;     // Laplace / Phase: update the temporal state but skip synthesis + egress (*produced = 0); used by the
                             // state-carry pass of temporal sharding (lvm_b200.shard.magnify_segment)
 };
 

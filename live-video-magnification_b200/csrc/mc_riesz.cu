@@ -562,6 +562,10 @@ mc_status RieszMode::process(const ModeCtx& ctx, const FrameIO& io, const mc_par
         std::swap(cur_rx[(size_t)i], old_rx[(size_t)i]);
         std::swap(cur_ry[(size_t)i], old_ry[(size_t)i]);
     }
+    if (ctx.analysis_only) {   // state-carry pass of temporal sharding: pyramids and filter registers are up to date
+        *produced = 0;
+        return MC_OK;
+    }
     // amplify (RieszPyramid.cpp:248-252) — this frame's band/pair now live in the old_* buffers
     const float alpha = (float)p.amplification;
     const float thresh = (float)(p.coWavelength * (3.14159265358979323846 / 100.0));  // PI_PERCENT, :214,:269

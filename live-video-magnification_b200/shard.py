@@ -272,6 +272,8 @@ def magnify_segment(frames, cfg, rank: int, world: int, make_processor, send, re
     elif mode == int(MagnificationMode.Phase):
         if rank > 0 and len(preroll) < 1:
             raise ValueError("Phase needs the (up to two) frames preceding the segment as pre-roll")
+        if rank > 0:
+            proc.set_option("analysis_only", 1)  # first pass: pyramids + filter registers only, no amplify / collapse / egress
         run(preroll[-2:])                       # frame 1 initialises (passthrough), frame 2 completes the prior pyramid
         first_state = export_riesz_state(proc)  # x_pre (all zero when there is a single pre-roll frame)
         outs = run(frames)                      # rank 0: final; rank > 0: first pass
@@ -285,6 +287,7 @@ def magnify_segment(frames, cfg, rank: int, world: int, make_processor, send, re
             send(_pack(true_end)[1], rank + 1)
         if rank > 0:
             proc.reset()
+            proc.set_option("analysis_only", 0)
             run(preroll[-2:])
             import_motion_state(proc, prev_true)   # same name/level -> plane protocol
             outs = run(frames)
