@@ -119,9 +119,13 @@ def export_motion_state(proc, max_levels: int = 16):
     return out
 
 
-def import_motion_state(proc, state) -> None:
+def import_state(proc, state) -> None:
+    """{(name, level): planes} -> mc_set_state, for either mode's state planes."""
     for (name, lvl), a in state.items():
         proc.set_state(name, lvl, a)
+
+
+import_motion_state = import_state   # earlier name
 
 
 def carry_motion_state(end_state, first_state, prev_true_state, n_frames: int, co_low: float, co_high: float):
@@ -267,7 +271,7 @@ def magnify_segment(frames, cfg, rank: int, world: int, make_processor, send, re
             proc.reset()
             proc.set_option("analysis_only", 0)
             proc.process_image(frames[0], cfg)
-            import_motion_state(proc, prev_true)
+            import_state(proc, prev_true)
             outs = run(frames)
     elif mode == int(MagnificationMode.Phase):
         if rank > 0 and len(preroll) < 1:
@@ -289,7 +293,7 @@ def magnify_segment(frames, cfg, rank: int, world: int, make_processor, send, re
             proc.reset()
             proc.set_option("analysis_only", 0)
             run(preroll[-2:])
-            import_motion_state(proc, prev_true)   # same name/level -> plane protocol
+            import_state(proc, prev_true)
             outs = run(frames)
     else:
         raise NotImplementedError("mode None has nothing to shard")
