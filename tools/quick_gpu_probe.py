@@ -26,8 +26,9 @@ def main():
     from oracle import livim_oracle as O, livim_ref
     from common import make_cfgs
     out = {}
+    pw, ph = int(os.environ.get("PROBE_W", "1920")), int(os.environ.get("PROBE_H", "1080"))
     R = livim_ref.load()
-    for (w, h, levels, n) in ((320, 240, 4, 6), (1920, 1080, 6, 3)):
+    for (w, h, levels, n) in ((320, 240, 4, 6), (pw, ph, 6, 3)):
         cfg, ocfg = make_cfgs(O.MODE_LAPLACE, 20, 50.0, 0.4, 3.0, 30, levels)
         proc = L.MagnificationProcessor(0)
         ref = R.Processor() if R is not None else O.MagnificationProcessor()
@@ -42,7 +43,7 @@ def main():
         out[f"parity_{w}x{h}"] = {"max_u8_diff": worst, "differing": ndiff, "checker": "reference" if R is not None else "oracle"}
         proc.close()
     cfg, _ = make_cfgs(O.MODE_LAPLACE, 20, 50.0, 0.4, 3.0, 0, 6)
-    base = [synth_frame(t, 1920, 1080, 3) for t in range(2)]
+    base = [synth_frame(t, pw, ph, 3) for t in range(2)]
 
     def table_for(lanes, options):
         clip = [np.stack([np.roll(base[t], (11 * k, 37 * k), axis=(0, 1)) for k in range(lanes)]) for t in range(2)]
