@@ -46,7 +46,6 @@ __constant__ float c_lp[81] = {
 };
 
 constexpr int RT_W = 32, RT_H = 16;                 // output tile
-constexpr int RA_W = RT_W + 8, RA_H = RT_H + 8;     // + 4 halo for 9x9
 
 __device__ __forceinline__ float mulr(float a, float b) { return __fmul_rn(a, b); }
 __device__ __forceinline__ float addr(float a, float b) { return __fadd_rn(a, b); }
