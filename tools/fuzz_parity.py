@@ -101,7 +101,7 @@ def main():
     args = ap.parse_args()
     if os.environ.get("MC_EMU") == "1":
         import conftest
-        conftest.use_emulated_library()
+        conftest.use_emulated_library(asan=os.environ.get("MC_EMU_ASAN") == "1")
     if args.chain:
         return fuzz_chain(args)
     import lvm_b200 as L
