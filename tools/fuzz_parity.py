@@ -156,7 +156,7 @@ def main():
             for t, f in enumerate(frames):
                 if t == change_at:   # non-structural change: same levels, new alpha / cutoffs / wavelength / chroma
                     u2 = params()
-                    ui2 = (u2[0], u2[1], u2[2], u2[3], u2[4], ui[5])
+                    ui2 = (u2[0], u2[1], u2[2], min(u2[3], fps / 2) if mode == O.MODE_PHASE else u2[3], u2[4], ui[5])
                     desc += f" ui2={ui2}"
                     cfg, ocfg = make_cfgs(mode, *ui2, fps)
                     rcfg = livim_ref.to_ref_config(R, ocfg) if R is not None else ocfg
