@@ -164,6 +164,7 @@ void launch(dim3 grid, dim3 block, size_t smem, void*, const char* name, const s
     if (g_in_kernel) die("nested launch", name);
     if (smem > 227 * 1024) die("more than 227 KB of dynamic shared memory", name);
     g_dyn_smem = smem ? std::aligned_alloc(128, (smem + 127) / 128 * 128) : nullptr;   // fresh per launch: ASan sees overruns
+    if (g_dyn_smem) std::memset(g_dyn_smem, 0xcd, smem);                               // shared memory starts as garbage
     const unsigned n = block.x * block.y * block.z;
     if (n == 0 || n > 1024) die("bad block size", name);
     if (grid.x == 0 || grid.y == 0 || grid.z == 0 || grid.y > 65535 || grid.z > 65535) die("bad grid size", name);
