@@ -75,3 +75,24 @@ def test_chain_front_stages_on_emulation(emu):
         ocur, oorig, _, _ = O.run_chain_once(omag, f, ocfg)
         assert np.array_equal(orig.image, oorig), t
         assert int(u8_diff(cur.image, ocur).max()) <= 1, t
+
+
+@pytest.mark.parametrize("env", [{}, {"CUDA_EMU_ORDER": "reverse"}, {"CUDA_EMU_ORDER": "random"}, {"CUDA_EMU_ASYNC": "1"},
+                                 {"CUDA_EMU_ASYNC": "1", "CUDA_EMU_ORDER": "random", "CUDA_EMU_SEED": "5"}],
+                         ids=["default", "reverse", "random", "async", "async+random"])
+def test_emulation_selftest(env):
+    """The emulation itself against closed forms (tests/cuda_emu/selftest): warp shuffles with lanes that exit after
+    taking part, barriers with exited threads, two TMA loads (one partly out of bounds) on one mbarrier with transaction
+    counting, the tensor-map encoder's alignment rules, atomics, and a producer/consumer pair on two streams — which must
+    be right with its event wait in every mode and observably wrong without it when streams run asynchronously."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    d = os.path.join(root, "tests", "cuda_emu", "selftest")
+    exe = os.path.join(d, "selftest")
+    srcs = [os.path.join(d, "selftest.cpp"), os.path.join(root, "tests", "cuda_emu", "emu_runtime.cpp")]
+    if not os.path.exists(exe) or any(os.path.getmtime(s) > os.path.getmtime(exe) for s in srcs):
+        subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-I", os.path.join(root, "tests", "cuda_emu", "include"), *srcs, "-o", exe],
+                       check=True)
+    r = subprocess.run([exe], env={**os.environ, **env}, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "selftest: ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
