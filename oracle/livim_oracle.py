@@ -11,8 +11,8 @@ tschnz/Live-Video-Magnification behind ``MagnificationProcessor::process``:
   * src/processing/MagnificationProcessor.cpp        (level clamp, structural reset, passthrough)
   * src/processing/MagnificationParamsUi.hpp         (UI Hz / % -> algorithm units)
 
-Every function cites the reference file:line it follows. Only ``tests/``, ``__graft_entry__.smoke()``
-and ``bench.py``'s cpu_baseline / ``--impl reference`` legs may import this module.
+Every function cites the reference file:line it follows. Only ``tests/`` (its helper scripts under ``tests/tools/``
+included), ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference`` legs may import this module.
 
 PARITY PIN STATUS: the reference ships no tests, golden vectors or fixtures for this path (SURVEY.md §4,
 §8c), and its CMake/vcpkg build cannot run here (no OpenCV C++ headers or libraries, no Qt).  The oracle is

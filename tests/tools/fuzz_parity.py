@@ -3,9 +3,9 @@
 modes, levels and parameters — with mid-stream parameter changes and resets — through the CUDA path and the checker
 (the reference's compiled code, oracle/_ref, else the oracle).  Prints every case that breaks the tolerances.
 
-    MC_EMU=1 python tools/fuzz_parity.py --cases 200 --seed 0      # on the CUDA-on-CPU emulation (no GPU)
-    python tools/fuzz_parity.py --cases 500                         # on a B200
-    MC_EMU=1 python tools/fuzz_parity.py --chain --cases 500        # the fused front of the chain (ROI / INTER_AREA /
+    MC_EMU=1 python tests/tools/fuzz_parity.py --cases 200 --seed 0      # on the CUDA-on-CPU emulation (no GPU)
+    python tests/tools/fuzz_parity.py --cases 500                         # on a B200
+    MC_EMU=1 python tests/tools/fuzz_parity.py --chain --cases 500        # the fused front of the chain (ROI / INTER_AREA /
                                                                     # gray): original tap bit-exact, frame <= 1 LSB
 """
 import argparse
@@ -15,7 +15,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 

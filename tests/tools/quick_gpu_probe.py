@@ -3,8 +3,8 @@
 small and a 1080p clip, then the per-kernel device-time table (profile_kernels) of the 1080p bench workload through
 the blocking host API.  Prints one JSON line.
 
-    python tools/quick_gpu_probe.py                 # parity + one table (PROBE_LANES, default 8)
-    python tools/quick_gpu_probe.py --ab 8,32       # A/B of the kernel options at those lane counts:
+    python tests/tools/quick_gpu_probe.py                 # parity + one table (PROBE_LANES, default 8)
+    python tests/tools/quick_gpu_probe.py --ab 8,32       # A/B of the kernel options at those lane counts:
                                                     # default | prefetch_state | egress_tma | use_tail | all three | band_from_state | ...
 """
 import json
@@ -14,7 +14,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 

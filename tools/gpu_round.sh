@@ -10,7 +10,7 @@ mode=${1:-full}
 log() { echo "[gpu_round] $*" | tee -a gpurun_out/gpu_round.log; }
 
 log "1. torch-free parity probe + A/B of the off-by-default kernel options (8 and 32 lanes)"
-timeout 240 python tools/quick_gpu_probe.py --ab 8,32 > gpurun_out/ab_probe.json 2> gpurun_out/ab_probe.err; log "   rc=$?"
+timeout 240 python tests/tools/quick_gpu_probe.py --ab 8,32 > gpurun_out/ab_probe.json 2> gpurun_out/ab_probe.err; log "   rc=$?"
 [ "$mode" = quick ] && exit 0
 
 log "2. GPU parity suite (default paths), then the experimental-option tests"
@@ -33,5 +33,5 @@ for k in k_ingest_lab k_egress k_level; do
 done
 
 log "6. randomised parity on the hardware (5 min)"
-timeout 300 python tools/fuzz_parity.py --cases 300 --seed 101 --max-size 400 > gpurun_out/fuzz_gpu.log 2>&1; log "   rc=$?"
+timeout 300 python tests/tools/fuzz_parity.py --cases 300 --seed 101 --max-size 400 > gpurun_out/fuzz_gpu.log 2>&1; log "   rc=$?"
 log "done"
