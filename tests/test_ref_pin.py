@@ -238,7 +238,7 @@ def test_dropin_chain_builds_against_real_reference_headers_and_has_no_cpu_fallb
     Frame.hpp.  Without a GPU constructing it must fail loudly: mc_create reports no device, the adapter throws."""
     import torch
     if torch.cuda.is_available():
-        pytest.skip("GPU present: covered by tests/test_gpu_vs_reference.py::test_dropin_chain_on_gpu")
+        pytest.skip("GPU present: covered by tests/test_gpu_zz_vs_reference.py::test_dropin_chain_on_gpu")
     R.set_magcore_library(built[0])
     with pytest.raises(RuntimeError, match="magcore_b200"):
         R.DropInChain(0)
