@@ -43,10 +43,30 @@ def main():
         out[f"parity_{w}x{h}"] = {"max_u8_diff": worst, "differing": ndiff, "checker": "reference" if R is not None else "oracle"}
         proc.close()
     cfg, _ = make_cfgs(O.MODE_LAPLACE, 20, 50.0, 0.4, 3.0, 0, 6)
-    base = [synth_frame(t, pw, ph, 3) for t in range(2)]
+    # PROBE_CLIP: what the frames look like.  "synthetic" = the bench clip (six gratings down to 8 px + noise: neighbouring
+    # pixels often fall into different cells of the Lab LUT), "smooth" = a natural-video-like gradient field with +-1
+    # noise, "noise" = white noise (worst case for the LUT gathers).  Comparing ingest_lab across them shows how much of
+    # its time is L1 wavefronts of the exact-LUT gathers (the hypothesis behind a lane mapping with 32 adjacent pixels).
+    kind = os.environ.get("PROBE_CLIP", "synthetic")
+    if kind == "synthetic":
+        base = [synth_frame(t, pw, ph, 3) for t in range(2)]
+    else:
+        rng = np.random.default_rng(0)
+        yy, xx = np.mgrid[0:ph, 0:pw]
+        base = []
+        for t in range(2):
+            if kind == "smooth":
+                g = 128 + 60 * np.sin(xx / 180.0 + 0.1 * t) * np.cos(yy / 140.0)
+                f = g[..., None] + np.array([0.0, 12.0, -18.0]) + rng.integers(-1, 2, size=(ph, pw, 3))
+            else:
+                f = rng.integers(0, 256, size=(ph, pw, 3)).astype(np.float64)
+            base.append(np.clip(np.rint(f), 0, 255).astype(np.uint8))
+    out["clip"] = kind
 
     def table_for(lanes, options):
         clip = [np.stack([np.roll(base[t], (11 * k, 37 * k), axis=(0, 1)) for k in range(lanes)]) for t in range(2)]
+        if lanes == 1:
+            clip = [c[0] for c in clip]          # a single stream takes plain HxWxC frames
         proc = L.MagnificationProcessor(0, lanes=lanes)
         for k, v in options.items():
             proc.set_option(k, v)

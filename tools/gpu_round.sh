@@ -11,6 +11,9 @@ log() { echo "[gpu_round] $*" | tee -a gpurun_out/gpu_round.log; }
 
 log "1. torch-free parity probe + A/B of the off-by-default kernel options (8 and 32 lanes)"
 timeout 240 python tests/tools/quick_gpu_probe.py --ab 8,32 > gpurun_out/ab_probe.json 2> gpurun_out/ab_probe.err; log "   rc=$?"
+for clip in smooth noise; do   # how content-dependent is the exact-LUT ingest kernel?
+    PROBE_CLIP=$clip PROBE_LANES=8 timeout 120 python tests/tools/quick_gpu_probe.py > gpurun_out/probe_$clip.json 2> gpurun_out/probe_$clip.err; log "   clip $clip rc=$?"
+done
 [ "$mode" = quick ] && exit 0
 
 log "2. GPU parity suite (default paths), then the experimental-option tests"
