@@ -163,6 +163,9 @@ void* mc_stream(mc_handle* h);
  *   "use_tail" (default 0): Laplace — the coarse pyramid levels whose planes together fit one CTA's shared memory
  *        (levels >= 3 at 1080p) are analysed, filtered and collapsed by one kernel launch instead of one launch per
  *        level and direction (results within float rounding of the per-level kernels; for A/B measurements)
+ *   "ingest_compact" (default 0): the fused BGR->Lab ingest routes each row through shared memory so that one gather
+ *        instruction of the exact OpenCV Lab LUT serves 32 adjacent pixels instead of 32 pixels four columns apart
+ *        (same results; fewer L1 wavefronts on coherent content; for A/B measurements)
  *   "egress_tma" (default 0; needs use_tma; 3-channel frames): the egress kernel requests its Lab16 tile, its level-1
  *        band window and its level-2 window as TMA bulk copies at kernel entry (same results; for A/B measurements)
  *   "analysis_only" (default 0): Laplace and Phase — frames after the first update the temporal state (EMA planes;

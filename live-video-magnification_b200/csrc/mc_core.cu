@@ -45,7 +45,7 @@ struct mc_handle {
     float t_rx = 0.f, t_ry = 0.f, t_rw = 1.f, t_rh = 1.f;
 
     // options
-    bool faithful0 = false, keep_float = false, profile = false, use_tma = true, prefetch_state = false, use_tail = false, egress_tma = false, band_from_state = false, analysis_only = false;
+    bool faithful0 = false, keep_float = false, profile = false, use_tma = true, prefetch_state = false, use_tail = false, ingest_compact = false, egress_tma = false, band_from_state = false, analysis_only = false;
     Profiler prof;
     int depth = 3;
 
@@ -188,7 +188,7 @@ mc_status process_device_impl(mc_handle* h, const uint8_t* d_in, int w, int hh, 
         fout = h->float_out;
     }
 
-    ModeCtx ctx{h->stream, &h->tables, &h->launches, &h->err, h->faithful0, fout, h->profile ? &h->prof : nullptr, h->use_tma, h->prefetch_state, h->use_tail, h->egress_tma, h->band_from_state, h->analysis_only};
+    ModeCtx ctx{h->stream, &h->tables, &h->launches, &h->err, h->faithful0, fout, h->profile ? &h->prof : nullptr, h->use_tma, h->prefetch_state, h->use_tail, h->ingest_compact, h->egress_tma, h->band_from_state, h->analysis_only};
     mc_status st = MC_OK;
     switch (p->mode) {
         case MC_MODE_LAPLACE: st = h->motion.process(ctx, io, *p, levels, produced); break;
@@ -371,6 +371,7 @@ mc_status mc_set_option(mc_handle* h, const char* key, int value) {
     if (!std::strcmp(key, "use_tma")) { h->use_tma = value != 0; return MC_OK; }
     if (!std::strcmp(key, "prefetch_state")) { h->prefetch_state = value != 0; return MC_OK; }
     if (!std::strcmp(key, "use_tail")) { h->use_tail = value != 0; return MC_OK; }
+    if (!std::strcmp(key, "ingest_compact")) { h->ingest_compact = value != 0; return MC_OK; }
     if (!std::strcmp(key, "egress_tma")) { h->egress_tma = value != 0; return MC_OK; }
     if (!std::strcmp(key, "band_from_state")) { h->band_from_state = value != 0; return MC_OK; }
     if (!std::strcmp(key, "analysis_only")) { h->analysis_only = value != 0; return MC_OK; }

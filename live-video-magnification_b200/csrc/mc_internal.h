@@ -63,7 +63,7 @@ cudaError_t launch_lab16(const FrameIO& io, const DeviceTables& tb, int16_t* lab
 
 // fused ingest of the production path: u8 BGR -> Lab16 planes + G1 = pyrDown(Lab) (MagnifyCore.hpp:87-96, level 0)
 cudaError_t launch_ingest_lab(const FrameIO& io, const DeviceTables& tb, int16_t* lab, int pitch16, size_t plane16,
-                              float* g1, const Level& l1, cudaStream_t s);
+                              float* g1, const Level& l1, cudaStream_t s, bool compact = false);
 
 struct LevelArgs {
     int in_kind = 0;           // 0: f32 planes, 1: Lab int16 planes, 2: u8 gray frame

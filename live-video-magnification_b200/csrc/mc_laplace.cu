@@ -478,9 +478,15 @@ struct IngestArgs {
 
 struct Lab4 { float L[4], A[4], B[4]; };
 
+// COMPACT (option ingest_compact): the LUT gathers are the kernel's bottleneck (L1 wavefronts: every distinct 128-byte
+// line a warp-wide load touches costs one).  With the natural mapping the 32 lanes of one gather instruction hold pixels
+// 4 columns apart across a 128-pixel span; in COMPACT mode the row's pixels take a detour through shared memory so that
+// each gather instruction serves 32 ADJACENT pixels (which share LUT cells far more often), and the lanes pick up
+// their own four columns afterwards.  Same values, bit for bit.
+template <bool COMPACT>
 __device__ __forceinline__ void ig_row(const IngestArgs& a, const uint16_t* s_tx, const uint8_t* frame, int row, int gx,
                                        bool fast, bool own, int16_t* lab_lane, float (&hL)[2], float (&hA)[2],
-                                       float (&hB)[2]) {
+                                       float (&hB)[2], uint32_t* s_raw, short (*s_lab)[128]) {
     // loads 4 BGR pixels of fine row `row` (reflected), converts, optionally stores Lab16, returns the row pass
     const int ry = reflect101(row, a.h);
     const uint8_t* p = frame + (size_t)ry * a.in_step;
@@ -502,9 +508,34 @@ __device__ __forceinline__ void ig_row(const IngestArgs& a, const uint16_t* s_tx
         }
     }
     int sL[4], sA[4], sB[4];
+    if (COMPACT) {
+        const int lane = threadIdx.x & 31;
+        // the lane's 12 bytes -> strip order in shared memory (3 words per lane)
+        s_raw[3 * lane] = px[0] | (px[1] << 8) | (px[2] << 16) | (px[3] << 24);
+        s_raw[3 * lane + 1] = px[4] | (px[5] << 8) | (px[6] << 16) | (px[7] << 24);
+        s_raw[3 * lane + 2] = px[8] | (px[9] << 8) | (px[10] << 16) | (px[11] << 24);
+        __syncwarp();
+        const uint8_t* rb = reinterpret_cast<const uint8_t*>(s_raw);
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-        lab_fixed_from_tx(s_tx[px[3 * i]], s_tx[px[3 * i + 1]], s_tx[px[3 * i + 2]], a.lut, sL[i], sA[i], sB[i]);
+        for (int i = 0; i < 4; ++i) {
+            const int p = lane + 32 * i;            // 32 adjacent pixels per gather instruction
+            int cl, ca, cb;
+            lab_fixed_from_tx(s_tx[rb[3 * p]], s_tx[rb[3 * p + 1]], s_tx[rb[3 * p + 2]], a.lut, cl, ca, cb);
+            s_lab[0][p] = (short)cl; s_lab[1][p] = (short)ca; s_lab[2][p] = (short)cb;
+        }
+        __syncwarp();
+        const short4 qL = *reinterpret_cast<const short4*>(&s_lab[0][4 * lane]);
+        const short4 qA = *reinterpret_cast<const short4*>(&s_lab[1][4 * lane]);
+        const short4 qB = *reinterpret_cast<const short4*>(&s_lab[2][4 * lane]);
+        sL[0] = qL.x; sL[1] = qL.y; sL[2] = qL.z; sL[3] = qL.w;
+        sA[0] = qA.x; sA[1] = qA.y; sA[2] = qA.z; sA[3] = qA.w;
+        sB[0] = qB.x; sB[1] = qB.y; sB[2] = qB.z; sB[3] = qB.w;
+        __syncwarp();                               // the buffers are reused by the next row
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            lab_fixed_from_tx(s_tx[px[3 * i]], s_tx[px[3 * i + 1]], s_tx[px[3 * i + 2]], a.lut, sL[i], sA[i], sB[i]);
+    }
     if (own) {   // this warp owns the row and the lane owns the columns: emit the Lab16 planes
         int16_t* o = lab_lane + (size_t)row * a.pitch16 + gx;
         *reinterpret_cast<short4*>(o) = make_short4((short)sL[0], (short)sL[1], (short)sL[2], (short)sL[3]);
@@ -524,11 +555,16 @@ __device__ __forceinline__ void ig_row(const IngestArgs& a, const uint16_t* s_tx
     o = ds_rowpass(r); hB[0] = o.h0; hB[1] = o.h1;
 }
 
+template <bool COMPACT>
 __global__ void __launch_bounds__(32 * IG_WARPS) k_ingest_lab(const IngestArgs a) {
     __shared__ uint16_t s_tx[256];
+    __shared__ __align__(16) uint32_t s_raw_all[COMPACT ? IG_WARPS : 1][COMPACT ? 96 : 1];
+    __shared__ __align__(16) short s_lab_all[COMPACT ? IG_WARPS : 1][COMPACT ? 3 : 1][128];
     for (int i = threadIdx.x; i < 256; i += 32 * IG_WARPS) s_tx[i] = (uint16_t)lab_tx_of_u8(i);
     __syncthreads();
     const int lane_id = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t* s_raw = s_raw_all[COMPACT ? warp : 0];
+    short (*s_lab)[128] = s_lab_all[COMPACT ? warp : 0];
     const int lane = blockIdx.z;                                       // stream
     const int gx = blockIdx.x * DS_COLS - 4 + lane_id * 4;
     const int k0 = (blockIdx.y * IG_WARPS + warp) * IG_ROWS;
@@ -548,13 +584,13 @@ __global__ void __launch_bounds__(32 * IG_WARPS) k_ingest_lab(const IngestArgs a
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int row = 2 * k0 - 2 + i;
-        ig_row(a, s_tx, frame, row, gx, fast, col_owner && row >= 2 * k0 && row < a.h, lab_lane, wL[i], wA[i], wB[i]);
+        ig_row<COMPACT>(a, s_tx, frame, row, gx, fast, col_owner && row >= 2 * k0 && row < a.h, lab_lane, wL[i], wA[i], wB[i], s_raw, s_lab);
     }
     for (int k = k0; k < k_end; ++k) {
         float nL[2], nA[2], nB[2];
         {
             const int row = 2 * k + 2;
-            ig_row(a, s_tx, frame, row, gx, fast, col_owner && row < 2 * k_end && row < a.h, lab_lane, nL, nA, nB);
+            ig_row<COMPACT>(a, s_tx, frame, row, gx, fast, col_owner && row < 2 * k_end && row < a.h, lab_lane, nL, nA, nB, s_raw, s_lab);
         }
         if (writer) {
             float* q = oL + (size_t)k * a.l1.pitch + jx;
@@ -575,7 +611,7 @@ __global__ void __launch_bounds__(32 * IG_WARPS) k_ingest_lab(const IngestArgs a
         {
             const int row = 2 * k + 3;
             const bool need = k + 1 < k_end;   // the last iteration's extra row is never used
-            if (need) ig_row(a, s_tx, frame, row, gx, fast, col_owner && row < 2 * k_end && row < a.h, lab_lane, mL, mA, mB);
+            if (need) ig_row<COMPACT>(a, s_tx, frame, row, gx, fast, col_owner && row < 2 * k_end && row < a.h, lab_lane, mL, mA, mB, s_raw, s_lab);
             else { mL[0] = mL[1] = mA[0] = mA[1] = mB[0] = mB[1] = 0.f; }
         }
 #pragma unroll
@@ -1030,14 +1066,15 @@ cudaError_t launch_lab16(const FrameIO& io, const DeviceTables& tb, int16_t* lab
 }
 
 cudaError_t launch_ingest_lab(const FrameIO& io, const DeviceTables& tb, int16_t* lab, int pitch16, size_t plane16,
-                              float* g1, const Level& l1, cudaStream_t s) {
+                              float* g1, const Level& l1, cudaStream_t s, bool compact) {
     IngestArgs a;
     a.in = io.in; a.in_step = io.in_step; a.in_lane_stride = io.in_lane_stride;
     a.w = io.w; a.h = io.h;
     a.aligned = (reinterpret_cast<uintptr_t>(io.in) % 4 == 0) && (io.in_step % 4 == 0) && (io.in_lane_stride % 4 == 0);
     a.lut = tb.lab_lut; a.lab = lab; a.pitch16 = pitch16; a.plane16 = plane16; a.g1 = g1; a.l1 = l1;
     dim3 grid(cdiv(io.w, DS_COLS), cdiv(l1.h, IG_ROWS * IG_WARPS), io.lanes);
-    k_ingest_lab<<<grid, 32 * IG_WARPS, 0, s>>>(a);
+    if (compact) k_ingest_lab<true><<<grid, 32 * IG_WARPS, 0, s>>>(a);
+    else k_ingest_lab<false><<<grid, 32 * IG_WARPS, 0, s>>>(a);
     return cudaGetLastError();
 }
 

@@ -39,6 +39,8 @@ struct ModeCtx {
                             // until measured on the B200)
     bool use_tail;          // levels >= MotionMode::tail_start run in the single fused tail kernel (option "use_tail", default off
                             // until measured on the B200)
+    bool ingest_compact;    // ingest: each LUT gather instruction serves 32 adjacent pixels (option "ingest_compact", default off
+                            // until measured on the B200)
     bool egress_tma;        // egress requests its three tile sources by TMA at kernel entry (option "egress_tma", default off
                             // until measured on the B200)
     bool band_from_state;   // synthesis rebuilds gain*(hi-lo) from the state planes instead of reading a stored band

@@ -109,7 +109,7 @@ mc_status MotionMode::process(const ModeCtx& ctx, const FrameIO& io, const mc_pa
     // ingest: u8 BGR -> Lab16 planes (gray frames are read directly by the level-0 kernel)
     // (production path, >= 2 levels: one fused kernel also builds G1; otherwise Lab16 alone)
     const bool fused_ingest = channels == 3 && !faithful && levels >= 2;
-    if (fused_ingest) LAUNCH("ingest_lab", 0, launch_ingest_lab(io, *ctx.tables, lab16, pitch16, plane16, G[1], lv[1], ctx.stream));
+    if (fused_ingest) LAUNCH("ingest_lab", 0, launch_ingest_lab(io, *ctx.tables, lab16, pitch16, plane16, G[1], lv[1], ctx.stream, ctx.ingest_compact));
     else if (channels == 3) LAUNCH("lab16", 0, launch_lab16(io, *ctx.tables, lab16, pitch16, plane16, ctx.stream));
 
     // analysis: one fused kernel per level (level 0 only builds G1 unless the faithful option is on)

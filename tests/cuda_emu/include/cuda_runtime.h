@@ -103,7 +103,7 @@ struct Launcher {
 
 // ---- synchronisation / warp intrinsics ----------------------------------------------------------------
 inline void __syncthreads() { cuda_emu::sync_threads(); }
-inline void __syncwarp(unsigned = 0xffffffffu) {}
+inline void __syncwarp(unsigned = 0xffffffffu) { cuda_emu::shfl(0, 0, 0, 32); }   // a shuffle is a warp barrier
 template <typename T> inline T emu_shfl_(T v, int arg, int mode, int width) {
     static_assert(sizeof(T) == 4, "32-bit shuffles only");
     unsigned b;

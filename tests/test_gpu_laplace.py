@@ -397,7 +397,7 @@ def test_fused_tail_option(w, h, c, levels):
 
 
 @pytest.mark.experimental
-@pytest.mark.parametrize("opts", [("use_tail", "prefetch_state", "egress_tma"), ("use_tail", "band_from_state", "prefetch_state"),
+@pytest.mark.parametrize("opts", [("use_tail", "prefetch_state", "egress_tma", "ingest_compact"), ("use_tail", "band_from_state", "prefetch_state"),
                                   ("use_tail", "faithful_level0"), ("prefetch_state", "egress_tma")])
 def test_option_combinations_agree_with_default(opts):
     """The A/B options compose: any combination gives the default path's frames (bit-identical without the fused
@@ -416,3 +416,20 @@ def test_option_combinations_agree_with_default(opts):
             assert int(d.max()) <= 1 and float((d == 0).mean()) >= 0.9999, (opts, t)
         else:
             assert int(d.max()) == 0, (opts, t)
+
+
+@pytest.mark.experimental
+def test_ingest_compact_option_equals_default():
+    """Option ingest_compact (every Lab-LUT gather instruction serves 32 adjacent pixels, via shared memory) must not
+    change a bit: outputs and state, interior and ragged strips (widths around the 120-column strip size), odd heights."""
+    for (w, h, lv) in [(640, 480, 4), (333, 251, 5), (121, 75, 3), (119, 64, 3), (240, 67, 2)]:
+        cfg, _ = make_cfgs(O.MODE_LAPLACE, 20, 50.0, 0.4, 3.0, 30, lv)
+        a, b = L.MagnificationProcessor(0), L.MagnificationProcessor(0)
+        b.set_option("ingest_compact", 1)
+        for t in range(3):
+            f = synth_frame(t, w, h, 3)
+            _, oa = a.process_image(f, cfg)
+            _, ob = b.process_image(f, cfg)
+            assert np.array_equal(oa, ob), (w, h, t)
+        for lvl in range(1, min(lv, L.calculateMaxLevels(w, h))):
+            assert np.array_equal(a.get_state("lowpassHi", lvl), b.get_state("lowpassHi", lvl)), (w, h, lvl)

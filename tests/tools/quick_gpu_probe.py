@@ -5,7 +5,7 @@ the blocking host API.  Prints one JSON line.
 
     python tests/tools/quick_gpu_probe.py                 # parity + one table (PROBE_LANES, default 8)
     python tests/tools/quick_gpu_probe.py --ab 8,32       # A/B of the kernel options at those lane counts:
-                                                    # default | prefetch_state | egress_tma | use_tail | all three | band_from_state | ...
+                                                    # default | prefetch_state | egress_tma | use_tail | ingest_compact | all four | band_from_state | ...
 """
 import json
 import os
@@ -85,8 +85,8 @@ def main():
     if "--ab" in sys.argv:
         lane_list = [int(x) for x in sys.argv[sys.argv.index("--ab") + 1].split(",")]
         out["ab"] = [table_for(n, o) for n in lane_list
-                     for o in ({}, {"prefetch_state": 1}, {"egress_tma": 1}, {"use_tail": 1},
-                               {"prefetch_state": 1, "egress_tma": 1, "use_tail": 1},
+                     for o in ({}, {"prefetch_state": 1}, {"egress_tma": 1}, {"use_tail": 1}, {"ingest_compact": 1},
+                               {"prefetch_state": 1, "egress_tma": 1, "use_tail": 1, "ingest_compact": 1},
                                {"band_from_state": 1}, {"prefetch_state": 1, "band_from_state": 1})]
     else:
         out.update(table_for(int(os.environ.get("PROBE_LANES", "8")), {}))

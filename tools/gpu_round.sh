@@ -18,7 +18,7 @@ done
 
 log "2. GPU parity suite (default paths), then the experimental-option tests"
 timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu.log 2>&1; log "   rc=$?"
-MC_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_laplace.py -q -m gpu -k "prefetch or egress_tma or fused_tail or option_combinations" \
+MC_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_laplace.py -q -m gpu -k "prefetch or egress_tma or fused_tail or ingest_compact or option_combinations" \
     > gpurun_out/pytest_experimental.log 2>&1; log "   experimental rc=$?"
 
 log "3. bench (N=1), both arms"
