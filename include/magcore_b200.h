@@ -31,8 +31,12 @@ typedef enum mc_status {
     MC_ERR_INVALID = 1,     /* bad argument */
     MC_ERR_CUDA = 2,        /* a CUDA runtime / cuFFT call failed; see mc_last_error() */
     MC_ERR_NO_DEVICE = 3,   /* no usable sm_100 device: the core has no CPU fallback */
-    MC_ERR_UNSUPPORTED = 4
+    MC_ERR_UNSUPPORTED = 4,
+    MC_ERR_INTERNAL = 5     /* a C++ exception (std::bad_alloc, ...) was caught at the boundary; the handle's temporal
+                               state has been dropped, as after any failed frame; see mc_last_error() */
 } mc_status;
+
+#define MC_MAX_LANES 4096   /* upper bound of mc_create_lanes(): lanes * channels is a CUDA grid.z extent */
 
 /* livim::MagnificationMode, src/processing/IProcessor.hpp:10 (same numeric order). */
 typedef enum mc_mode { MC_MODE_LAPLACE = 0, MC_MODE_PHASE = 1, MC_MODE_COLOR = 2, MC_MODE_NONE = 3 } mc_mode;
@@ -166,8 +170,6 @@ void* mc_stream(mc_handle* h);
  *   "ingest_compact" (default 0): the fused BGR->Lab ingest routes each row through shared memory so that one gather
  *        instruction of the exact OpenCV Lab LUT serves 32 adjacent pixels instead of 32 pixels four columns apart
  *        (same results; fewer L1 wavefronts on coherent content; for A/B measurements)
- *   "egress_tma" (default 0; needs use_tma; 3-channel frames): the egress kernel requests its Lab16 tile, its level-1
- *        band window and its level-2 window as TMA bulk copies at kernel entry (same results; for A/B measurements)
  *   "analysis_only" (default 0): Laplace and Phase — frames after the first update the temporal state (EMA planes;
  *        Riesz pyramids, phase accumulators and Butterworth registers) but skip synthesis and egress and report
  *        *produced = 0; the cheap first pass of temporal sharding

@@ -9,7 +9,8 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmagcore_b200.so")
 
-MC_OK, MC_ERR_INVALID, MC_ERR_CUDA, MC_ERR_NO_DEVICE, MC_ERR_UNSUPPORTED = 0, 1, 2, 3, 4
+MC_OK, MC_ERR_INVALID, MC_ERR_CUDA, MC_ERR_NO_DEVICE, MC_ERR_UNSUPPORTED, MC_ERR_INTERNAL = 0, 1, 2, 3, 4, 5
+MC_MAX_LANES = 4096
 MODE_LAPLACE, MODE_PHASE, MODE_COLOR, MODE_NONE = 0, 1, 2, 3
 
 

@@ -4,6 +4,7 @@
 // multiply -> C2R), global min-max normalisation, pyrUp chain (+ bilinear resize), min-max stretch.
 #include <cfloat>
 #include <cmath>
+#include <algorithm>
 #include <cstring>
 
 #include "mc_modes.h"
@@ -49,12 +50,19 @@ __global__ void k_ring_append(const float* __restrict__ src, int w, int h, int p
     }
 }
 
-// spectrum[k][i] *= mask[k]  (mulSpectrums with the CCS-packed 0/1 mask, TemporalFilter.cpp:45-48)
-__global__ void k_mask_mul(float2* __restrict__ spec, size_t S, int nbins, const float2* __restrict__ mask) {
-    const size_t n = S * nbins;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+// spectrum[k][i] *= mask[k]  (mulSpectrums with the CCS-packed 0/1 mask, TemporalFilter.cpp:45-48).
+// createIdealBandpassFilter (TemporalFilter.cpp:59-80) is a real 0/1 mask over the PACKED indices x (1 where
+// fl <= x <= fh); mulSpectrums reads it back as the complex number m[2k-1] + i m[2k] per bin, real only for DC and
+// Nyquist.  The mask is evaluated here from (fl, fh) — no host vector, no per-frame upload; `sc` carries DFT_SCALE of
+// both transforms.
+__global__ void k_mask_mul(float2* __restrict__ spec, size_t S, int nbins, int n, double fl, double fh, float sc) {
+    const size_t total = S * nbins;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int k = (int)(i / S);
-        const float2 m = mask[k];
+        const int xr = k == 0 ? 0 : (2 * k == n ? n - 1 : 2 * k - 1);
+        const bool has_im = k != 0 && 2 * k != n;
+        const float2 m = make_float2(((double)xr >= fl && (double)xr <= fh) ? sc : 0.0f,
+                                     (has_im && (double)(2 * k) >= fl && (double)(2 * k) <= fh) ? sc : 0.0f);
         const float2 v = spec[i];
         spec[i] = make_float2(v.x * m.x - v.y * m.y, v.x * m.y + v.y * m.x);
     }
@@ -205,18 +213,20 @@ inline unsigned gs_blocks(size_t n) {
 }  // namespace
 
 void ColorMode::reset() {
-    if (plan_r2c) cufftDestroy(plan_r2c);
-    if (plan_c2r) cufftDestroy(plan_c2r);
-    plan_r2c = plan_c2r = 0;
-    plan_n = 0;
+    for (auto& kv : plans) {
+        if (kv.second.r2c) cufftDestroy(kv.second.r2c);
+        if (kv.second.c2r) cufftDestroy(kv.second.c2r);
+    }
+    plans.clear();
+    plan_signals = 0;
+    fft_work = nullptr;      // owned by the arena
+    fft_work_bytes = 0;
     arena.release();
     lv.clear(); G.clear(); U.clear(); ulv.clear();
     ring = work = nullptr; spec = nullptr; minmax = nullptr;
     allocated = false;
     count = head = 0;
-    ring_cap = 0;
-    mask_dev = nullptr;
-    mask_cap = 0;
+    ring_cap = ring_mod = 0;
 }
 
 #define CUFFT_CK(call)                                                            \
@@ -262,21 +272,36 @@ mc_status ColorMode::process(const ModeCtx& ctx, const FrameIO& io, const mc_par
         allocated = true;
     }
     const size_t S = (size_t)planes * small_rows;  // signals (pixels x channels x lanes)
-    // ring capacity: grows when the framerate asks for a longer window (rare); contents are kept in
-    // logical order so the invariant "head == 0 or count == capacity" holds.
-    if (ring_cap < want_cap || ring == nullptr) {
-        const int new_cap = std::max(want_cap, std::max(ring_cap, 2));
-        float *nring = nullptr, *nwork = nullptr;
-        void* nspec = nullptr;
-        MCK(arena.alloc(&nring, (size_t)new_cap * S));
-        MCK(arena.alloc(&nwork, (size_t)new_cap * S));
-        MCK(arena.alloc_bytes(&nspec, sizeof(cufftComplex) * (size_t)(new_cap / 2 + 1) * S));
-        for (int t = 0; t < count; ++t)
-            MCK(cudaMemcpyAsync(nring + (size_t)t * S, ring + (size_t)((head + t) % ring_cap) * S, S * sizeof(float),
-                                cudaMemcpyDeviceToDevice, ctx.stream));
-        ring = nring; work = nwork; spec = (cufftComplex*)nspec;
+    // Ring geometry.  `ring_mod` is the LOGICAL ring size (slots are taken modulo it), `ring_cap` the allocation.  It
+    // follows the window cap the frame rate asks for; when that changes (rare: a UI action) the window is laid out
+    // once in logical order — into a bigger allocation when needed, the replaced buffers being freed — so that the
+    // invariant "head == 0 or count == ring_mod" holds from then on and no per-frame compaction is ever needed.  A
+    // window that is longer than a lowered cap keeps its length, as the reference's does (it drops one column per
+    // appended column, SpatialFilter.cpp:73-83).
+    const int want_mod = std::max(std::max(want_cap, count), 2);
+    if (ring == nullptr || want_mod != ring_mod) {
+        if (ring_cap < want_mod || ring == nullptr) {
+            float *nring = nullptr, *nwork = nullptr;
+            void* nspec = nullptr;
+            MCK(arena.alloc(&nring, (size_t)want_mod * S));
+            MCK(arena.alloc(&nwork, (size_t)want_mod * S));
+            MCK(arena.alloc_bytes(&nspec, sizeof(cufftComplex) * (size_t)(want_mod / 2 + 1) * S));
+            for (int t = 0; t < count; ++t)
+                MCK(cudaMemcpyAsync(nring + (size_t)t * S, ring + (size_t)((head + t) % ring_mod) * S, S * sizeof(float),
+                                    cudaMemcpyDeviceToDevice, ctx.stream));
+            if (ring) {   // cudaFree orders itself after the copies above (it synchronises the device)
+                arena.free_block(ring); arena.free_block(work); arena.free_block(spec);
+            }
+            ring = nring; work = nwork; spec = (cufftComplex*)nspec;
+            ring_cap = want_mod;
+        } else if (head != 0) {
+            for (int t = 0; t < count; ++t)
+                MCK(cudaMemcpyAsync(work + (size_t)t * S, ring + (size_t)((head + t) % ring_mod) * S, S * sizeof(float),
+                                    cudaMemcpyDeviceToDevice, ctx.stream));
+            std::swap(ring, work);
+        }
         head = 0;
-        ring_cap = new_cap;
+        ring_mod = want_mod;
     }
 
     // ingest + Gaussian chain (SpatialFilter.cpp:13-23)
@@ -297,7 +322,7 @@ mc_status ColorMode::process(const ModeCtx& ctx, const FrameIO& io, const mc_par
     // append to the rolling window; once full drop the oldest column (SpatialFilter.cpp:63-84)
     const Level& ls = lv[(size_t)levels];
     {
-        const int slot = (head + count) % ring_cap;
+        const int slot = (head + count) % ring_mod;
         const bool pp = ctx.prof && ctx.prof->begin("ring_append", 0, ctx.stream);
         k_ring_append<<<gs_blocks(S), 256, 0, ctx.stream>>>(G[(size_t)levels], ls.w, ls.h, ls.pitch, ls.plane, ring + (size_t)slot * S, planes);
         if (pp) ctx.prof->end(ctx.stream);
@@ -305,56 +330,64 @@ mc_status ColorMode::process(const ModeCtx& ctx, const FrameIO& io, const mc_par
         ++*ctx.launches;
         ++count;
         if (count > want_cap && want_cap > 0) {
-            head = (head + 1) % ring_cap;
+            head = (head + 1) % ring_mod;
             --count;
         }
     }
     if (count < 2) return MC_OK;  // MagnifyCore.hpp:180 (passthrough)
     const int n = count;
-    if (head != 0 && n != ring_cap) {
-        // The frame rate was lowered while the ring was only partly filled: the window no longer occupies a
-        // cyclically contiguous slot range.  Compact it into logical order (rare, so plain column copies).
-        for (int t = 0; t < n; ++t)
-            MCK(cudaMemcpyAsync(work + (size_t)t * S, ring + (size_t)((head + t) % ring_cap) * S, S * sizeof(float),
-                                cudaMemcpyDeviceToDevice, ctx.stream));
-        std::swap(ring, work);
-        head = 0;
-    }
 
-    // ideal temporal band-pass (TemporalFilter.cpp:24-57) on the physical column order
-    if (plan_n != n) {
-        if (plan_r2c) cufftDestroy(plan_r2c);
-        if (plan_c2r) cufftDestroy(plan_c2r);
-        plan_r2c = plan_c2r = 0;
+    // ideal temporal band-pass (TemporalFilter.cpp:24-57) on the physical column order.  The DFT length is the current
+    // window length (2 ... cap, every value once during warm-up): plans are cached per length and share one work area
+    // (they run one after another on the handle's stream), so warm-up costs one plan build per length per stream
+    // geometry instead of two cufftPlanMany + workspace malloc/free per frame.
+    if (plan_signals != S) {
+        for (auto& kv : plans) { cufftDestroy(kv.second.r2c); cufftDestroy(kv.second.c2r); }
+        plans.clear();
+        plan_signals = S;
+    }
+    auto it = plans.find(n);
+    if (it == plans.end()) {
+        FftPlans pl;
         int nn[1] = {n};
         int inembed[1] = {n}, onembed[1] = {n / 2 + 1};
-        CUFFT_CK(cufftPlanMany(&plan_r2c, 1, nn, inembed, (int)S, 1, onembed, (int)S, 1, CUFFT_R2C, (int)S));
-        CUFFT_CK(cufftPlanMany(&plan_c2r, 1, nn, onembed, (int)S, 1, inembed, (int)S, 1, CUFFT_C2R, (int)S));
-        CUFFT_CK(cufftSetStream(plan_r2c, ctx.stream));
-        CUFFT_CK(cufftSetStream(plan_c2r, ctx.stream));
-        plan_n = n;
+        size_t ws_a = 0, ws_b = 0;
+        CUFFT_CK(cufftCreate(&pl.r2c));
+        CUFFT_CK(cufftCreate(&pl.c2r));
+        it = plans.emplace(n, pl).first;   // owned from here on (reset() destroys them)
+        CUFFT_CK(cufftSetAutoAllocation(pl.r2c, 0));
+        CUFFT_CK(cufftSetAutoAllocation(pl.c2r, 0));
+        CUFFT_CK(cufftMakePlanMany(pl.r2c, 1, nn, inembed, (int)S, 1, onembed, (int)S, 1, CUFFT_R2C, (int)S, &ws_a));
+        CUFFT_CK(cufftMakePlanMany(pl.c2r, 1, nn, onembed, (int)S, 1, inembed, (int)S, 1, CUFFT_C2R, (int)S, &ws_b));
+        CUFFT_CK(cufftSetStream(pl.r2c, ctx.stream));
+        CUFFT_CK(cufftSetStream(pl.c2r, ctx.stream));
+        it->second.work_bytes = std::max(ws_a, ws_b);
+        if (it->second.work_bytes > fft_work_bytes) {
+            if (fft_work) arena.free_block(fft_work);
+            fft_work = nullptr;
+            fft_work_bytes = 0;
+            MCK(arena.alloc_bytes(&fft_work, it->second.work_bytes));
+            fft_work_bytes = it->second.work_bytes;
+            for (auto& kv : plans) kv.second.bound = nullptr;
+        }
     }
+    if (it->second.bound != fft_work) {
+        if (fft_work) {
+            CUFFT_CK(cufftSetWorkArea(it->second.r2c, fft_work));
+            CUFFT_CK(cufftSetWorkArea(it->second.c2r, fft_work));
+        }
+        it->second.bound = fft_work;
+    }
+    const cufftHandle plan_r2c = it->second.r2c, plan_c2r = it->second.c2r;
+    double mask_fl = 0, mask_fh = 0;
     {
         double lo = p.coLow, hi = p.coHigh;
         if (lo == 0.0) lo += 0.01;  // TemporalFilter.cpp:26-27
         // createIdealBandpassFilter (TemporalFilter.cpp:59-80): real 0/1 mask over packed indices x,
         // read back by mulSpectrums as the complex number m[2k-1] + i m[2k] per bin.
         const float width = (float)n;
-        const double fl = 2 * lo * width / p.framerate, fh = 2 * hi * width / p.framerate;
-        auto m = [&](int x) { return (x >= fl && x <= fh) ? 1.0f : 0.0f; };
-        std::vector<float2> mask((size_t)n / 2 + 1);
-        const float sc = 1.0f / ((float)n * (float)n);  // DFT_SCALE on both transforms
-        mask[0] = make_float2(m(0) * sc, 0.f);
-        for (int k = 1; k <= n / 2; ++k) {
-            if (2 * k == n) mask[(size_t)k] = make_float2(m(n - 1) * sc, 0.f);       // Nyquist: real only
-            else mask[(size_t)k] = make_float2(m(2 * k - 1) * sc, m(2 * k) * sc);
-        }
-        if (!mask_dev || mask_cap < (int)mask.size()) {
-            void* mv = nullptr;
-            MCK(arena.alloc_bytes(&mv, sizeof(float2) * (size_t)(ring_cap / 2 + 2)));
-            mask_dev = mv; mask_cap = ring_cap / 2 + 2;
-        }
-        MCK(cudaMemcpyAsync(mask_dev, mask.data(), sizeof(float2) * mask.size(), cudaMemcpyHostToDevice, ctx.stream));
+        mask_fl = 2 * lo * width / p.framerate;
+        mask_fh = 2 * hi * width / p.framerate;
     }
     {
         const bool pp = ctx.prof && ctx.prof->begin("cufft_r2c", 0, ctx.stream);
@@ -364,7 +397,8 @@ mc_status ColorMode::process(const ModeCtx& ctx, const FrameIO& io, const mc_par
     }
     {
         const bool pp = ctx.prof && ctx.prof->begin("mask_mul", 0, ctx.stream);
-        k_mask_mul<<<gs_blocks(S * (size_t)(n / 2 + 1)), 256, 0, ctx.stream>>>((float2*)spec, S, n / 2 + 1, (const float2*)mask_dev);
+        k_mask_mul<<<gs_blocks(S * (size_t)(n / 2 + 1)), 256, 0, ctx.stream>>>((float2*)spec, S, n / 2 + 1, n, mask_fl, mask_fh,
+                                                                                1.0f / ((float)n * (float)n));
         if (pp) ctx.prof->end(ctx.stream);
         MCK(cudaGetLastError());
         ++*ctx.launches;
@@ -376,7 +410,7 @@ mc_status ColorMode::process(const ModeCtx& ctx, const FrameIO& io, const mc_par
         ++*ctx.launches;
     }
     unsigned* mm = (unsigned*)minmax;
-    k_mm_init<<<1, 256, 0, ctx.stream>>>(mm, 4 * lanes);
+    k_mm_init<<<cdiv(4 * lanes, 256), 256, 0, ctx.stream>>>(mm, 4 * lanes);
     MCK(cudaGetLastError());
     ++*ctx.launches;
     {
@@ -390,7 +424,7 @@ mc_status ColorMode::process(const ModeCtx& ctx, const FrameIO& io, const mc_par
     }
     // the reconstructed column is logical index min(1, n-1) (MagnifyCore.hpp:189-192)
     const int logical = std::min(1, n - 1);
-    const int phys = (head + logical) % ring_cap;
+    const int phys = (head + logical) % ring_mod;
     {
         const bool pp = ctx.prof && ctx.prof->begin("select", 0, ctx.stream);
         k_select<<<gs_blocks(S), 256, 0, ctx.stream>>>(work + (size_t)phys * S, mm, C, ls.w, ls.h, (float)p.amplification, U[0], ulv[0].pitch, ulv[0].plane, planes);

@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstring>
 #include <deque>
+#include <new>
 #include <string>
 #include <vector>
 
@@ -45,7 +46,7 @@ struct mc_handle {
     float t_rx = 0.f, t_ry = 0.f, t_rw = 1.f, t_rh = 1.f;
 
     // options
-    bool faithful0 = false, keep_float = false, profile = false, use_tma = true, prefetch_state = false, use_tail = false, ingest_compact = false, egress_tma = false, band_from_state = false, analysis_only = false;
+    bool faithful0 = false, keep_float = false, profile = false, use_tma = true, prefetch_state = false, use_tail = false, ingest_compact = false, band_from_state = false, analysis_only = false;
     Profiler prof;
     int depth = 3;
 
@@ -67,6 +68,43 @@ struct mc_handle {
     std::deque<int> inflight;
     int next_slot = 0;
 };
+
+namespace {
+// ---- exception firewall of the C ABI ------------------------------------------------------------------------
+// include/magcore_b200.h promises that no C++ exception crosses the boundary (the reference's own firewall,
+// ProcessingChain.cpp:50-62, sits ABOVE the adapter and only understands what the adapter rethrows).  Every
+// extern "C" entry with a body that can allocate is a function-try-block ending in on_exception().
+thread_local int g_inject_throw = 0;   // test hook (mc_debug_inject_exception): >0 = throw at the n-th guarded entry
+
+inline void debug_maybe_throw() {
+    if (g_inject_throw > 0 && --g_inject_throw == 0) throw std::bad_alloc();
+}
+
+void reset_modes(mc_handle* h);
+void tracker_reset(mc_handle* h);
+
+mc_status on_exception(mc_handle* h) noexcept {
+    const char* what = "unknown C++ exception";
+    std::string buf;
+    try { throw; }
+    catch (const std::bad_alloc&) { what = "out of host memory (std::bad_alloc)"; }
+    catch (const std::exception& e) {
+        try { buf = std::string("C++ exception: ") + e.what(); what = buf.c_str(); } catch (...) {}
+    }
+    catch (...) {}
+    try {
+        if (h) {
+            h->err = what;
+            // the recovery contract of ProcessingChain.cpp:50-62: temporal state may be half-updated, drop it
+            reset_modes(h);
+            tracker_reset(h);
+        } else {
+            g_create_error = what;
+        }
+    } catch (...) {}
+    return MC_ERR_INTERNAL;
+}
+}  // namespace
 
 #define CK(call)                                                                                  \
     do {                                                                                          \
@@ -154,6 +192,7 @@ bool is_pinned(const void* p) {
 mc_status process_device_impl(mc_handle* h, const uint8_t* d_in, int w, int hh, int channels, size_t in_step,
                               const mc_params* p, uint8_t* d_out, size_t out_step, int* produced) {
     *produced = 0;
+    debug_maybe_throw();
     if (!p) { h->err = "params is null"; return MC_ERR_INVALID; }
     // Identity when disabled / empty; free state so a later re-enable starts cleanly (:21-29).
     if (p->mode == MC_MODE_NONE || d_in == nullptr || w <= 0 || hh <= 0) {
@@ -165,6 +204,7 @@ mc_status process_device_impl(mc_handle* h, const uint8_t* d_in, int w, int hh, 
     }
     if (p->mode < 0 || p->mode > MC_MODE_NONE) { h->err = "bad mode"; return MC_ERR_INVALID; }
     if (channels != 1 && channels != 3) { h->err = "channels must be 1 or 3"; return MC_ERR_INVALID; }
+    if (d_out == nullptr) { h->err = "output pointer is null"; return MC_ERR_INVALID; }
     if (in_step < (size_t)w * channels || out_step < (size_t)w * channels) { h->err = "step too small"; return MC_ERR_INVALID; }
     const int max_levels = calculate_max_levels(w, hh);  // :32-33
     if (max_levels < 1) return MC_OK;
@@ -188,7 +228,7 @@ mc_status process_device_impl(mc_handle* h, const uint8_t* d_in, int w, int hh, 
         fout = h->float_out;
     }
 
-    ModeCtx ctx{h->stream, &h->tables, &h->launches, &h->err, h->faithful0, fout, h->profile ? &h->prof : nullptr, h->use_tma, h->prefetch_state, h->use_tail, h->ingest_compact, h->egress_tma, h->band_from_state, h->analysis_only};
+    ModeCtx ctx{h->stream, &h->tables, &h->launches, &h->err, h->faithful0, fout, h->profile ? &h->prof : nullptr, h->use_tma, h->prefetch_state, h->use_tail, h->ingest_compact, h->band_from_state, h->analysis_only};
     mc_status st = MC_OK;
     switch (p->mode) {
         case MC_MODE_LAPLACE: st = h->motion.process(ctx, io, *p, levels, produced); break;
@@ -271,24 +311,27 @@ void mc_params_from_ui(mc_params* p, int mode, int amplification, double wavelen
 int mc_calculate_max_levels(int width, int height) { return calculate_max_levels(width, height); }
 int mc_optimal_buffer_size(int fps) { return optimal_buffer_size(fps); }
 
-mc_status mc_butterworth(unsigned order, double wn, double* a, double* b) {
+mc_status mc_butterworth(unsigned order, double wn, double* a, double* b) try {
+    debug_maybe_throw();
     if (!a || !b || order == 0 || order > 16) return MC_ERR_INVALID;
     std::vector<double> va, vb;
     butterworth(order, wn, va, vb);
     for (unsigned i = 0; i <= order; ++i) { a[i] = va[i]; b[i] = vb[i]; }
     return MC_OK;
-}
+} catch (...) { return on_exception(nullptr); }
 
-mc_status mc_motion_gains(const mc_params* p, int levels, int width, int height, float* gains) {
+mc_status mc_motion_gains(const mc_params* p, int levels, int width, int height, float* gains) try {
+    debug_maybe_throw();
     if (!p || !gains || levels < 1) return MC_ERR_INVALID;
     std::vector<float> g;
     motion_gains(p->amplification, p->coWavelength, levels, width, height, g);
     for (int i = 0; i <= levels; ++i) gains[i] = g[(size_t)i];
     return MC_OK;
-}
+} catch (...) { return on_exception(nullptr); }
 
-mc_status mc_create_lanes(int device, int lanes, mc_handle** out) {
-    if (!out || lanes < 1) { g_create_error = "bad arguments"; return MC_ERR_INVALID; }
+mc_status mc_create_lanes(int device, int lanes, mc_handle** out) try {
+    // grid.z carries lanes * channels (<= 65535) and the Color min/max scratch is sized per lane
+    if (!out || lanes < 1 || lanes > MC_MAX_LANES) { g_create_error = "bad arguments (1 <= lanes <= MC_MAX_LANES)"; return MC_ERR_INVALID; }
     *out = nullptr;
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0 || device < 0 || device >= n) {
@@ -302,7 +345,9 @@ mc_status mc_create_lanes(int device, int lanes, mc_handle** out) {
         g_create_error = "device is not sm_100-class; kernels are built for sm_100a only";
         return MC_ERR_NO_DEVICE;
     }
+    debug_maybe_throw();
     mc_handle* h = new mc_handle();
+    try {
     h->device = device;
     h->lanes = lanes;
     auto fail = [&](const char* what, cudaError_t e) {
@@ -328,11 +373,12 @@ mc_status mc_create_lanes(int device, int lanes, mc_handle** out) {
     h->motion.lanes = h->color.lanes = h->riesz.lanes = lanes;
     *out = h;
     return MC_OK;
-}
+    } catch (...) { mc_destroy(h); throw; }
+} catch (...) { return on_exception(nullptr); }
 
 mc_status mc_create(int device, mc_handle** out) { return mc_create_lanes(device, 1, out); }
 
-void mc_destroy(mc_handle* h) {
+void mc_destroy(mc_handle* h) try {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
@@ -352,18 +398,21 @@ void mc_destroy(mc_handle* h) {
     if (h->s_in) cudaStreamDestroy(h->s_in);
     if (h->s_out) cudaStreamDestroy(h->s_out);
     delete h;
-}
+} catch (...) {}
 
-mc_status mc_reset(mc_handle* h) {
+/* test hook, not declared in the public header: the n-th guarded entry on this thread throws std::bad_alloc */
+void mc_debug_inject_exception(int nth) { g_inject_throw = nth; }
+
+mc_status mc_reset(mc_handle* h) try {
     if (!h) return MC_ERR_INVALID;
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->stream));
     reset_modes(h);
     tracker_reset(h);
     return MC_OK;
-}
+} catch (...) { return on_exception(h); }
 
-mc_status mc_set_option(mc_handle* h, const char* key, int value) {
+mc_status mc_set_option(mc_handle* h, const char* key, int value) try {
     if (!h || !key) return MC_ERR_INVALID;
     if (!std::strcmp(key, "faithful_level0")) { h->faithful0 = value != 0; return MC_OK; }
     if (!std::strcmp(key, "keep_float_output")) { h->keep_float = value != 0; return MC_OK; }
@@ -372,7 +421,6 @@ mc_status mc_set_option(mc_handle* h, const char* key, int value) {
     if (!std::strcmp(key, "prefetch_state")) { h->prefetch_state = value != 0; return MC_OK; }
     if (!std::strcmp(key, "use_tail")) { h->use_tail = value != 0; return MC_OK; }
     if (!std::strcmp(key, "ingest_compact")) { h->ingest_compact = value != 0; return MC_OK; }
-    if (!std::strcmp(key, "egress_tma")) { h->egress_tma = value != 0; return MC_OK; }
     if (!std::strcmp(key, "band_from_state")) { h->band_from_state = value != 0; return MC_OK; }
     if (!std::strcmp(key, "analysis_only")) { h->analysis_only = value != 0; return MC_OK; }
     if (!std::strcmp(key, "pipeline_depth")) {
@@ -383,7 +431,7 @@ mc_status mc_set_option(mc_handle* h, const char* key, int value) {
     }
     h->err = std::string("unknown option ") + key;
     return MC_ERR_INVALID;
-}
+} catch (...) { return on_exception(h); }
 
 void* mc_stream(mc_handle* h) { return h ? (void*)h->stream : nullptr; }
 uint64_t mc_launch_count(mc_handle* h) { return h ? h->launches : 0; }
@@ -391,24 +439,24 @@ int mc_pipeline_depth(mc_handle* h) { return h ? h->depth : 0; }
 
 const char* mc_last_error(mc_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
-mc_status mc_sync(mc_handle* h) {
+mc_status mc_sync(mc_handle* h) try {
     if (!h) return MC_ERR_INVALID;
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->stream));
     return MC_OK;
-}
+} catch (...) { return on_exception(h); }
 
 mc_status mc_process_device(mc_handle* h, const uint8_t* d_in, int width, int height, int channels, size_t in_step,
-                            const mc_params* p, uint8_t* d_out, size_t out_step, int* produced) {
+                            const mc_params* p, uint8_t* d_out, size_t out_step, int* produced) try {
     if (!h || !produced) return MC_ERR_INVALID;
     CK(cudaSetDevice(h->device));
     return process_device_impl(h, d_in, width, height, channels, in_step, p, d_out, out_step, produced);
-}
+} catch (...) { return on_exception(h); }
 
 // submit with the destination known up front: when `in`/`out` are pinned (cudaHostAlloc /
 // cudaHostRegister) the copies go straight between the caller's buffers and HBM (no staging memcpy).
 mc_status mc_submit(mc_handle* h, const uint8_t* in, int width, int height, int channels, size_t in_step,
-                    const mc_params* p, uint8_t* out, size_t out_step) {
+                    const mc_params* p, uint8_t* out, size_t out_step) try {
     if (!h || !p) return MC_ERR_INVALID;
     CK(cudaSetDevice(h->device));
     if ((int)h->inflight.size() >= h->depth) { h->err = "pipeline full: call mc_collect first"; return MC_ERR_INVALID; }
@@ -465,9 +513,9 @@ mc_status mc_submit(mc_handle* h, const uint8_t* in, int width, int height, int 
     h->inflight.push_back(si);
     h->next_slot = (si + 1) % h->depth;
     return MC_OK;
-}
+} catch (...) { return on_exception(h); }
 
-mc_status mc_collect(mc_handle* h, int* produced) {
+mc_status mc_collect(mc_handle* h, int* produced) try {
     if (!h || !produced) return MC_ERR_INVALID;
     CK(cudaSetDevice(h->device));
     if (h->inflight.empty()) { h->err = "nothing in flight"; return MC_ERR_INVALID; }
@@ -481,19 +529,19 @@ mc_status mc_collect(mc_handle* h, int* produced) {
         for (size_t r = 0; r < rows; ++r) std::memcpy(s.user_out + r * s.user_out_step, s.h_out + r * row, row);
     }
     return MC_OK;
-}
+} catch (...) { return on_exception(h); }
 
 mc_status mc_process(mc_handle* h, const uint8_t* in, int width, int height, int channels, size_t in_step,
-                     const mc_params* p, uint8_t* out, size_t out_step, int* produced) {
+                     const mc_params* p, uint8_t* out, size_t out_step, int* produced) try {
     if (!h || !produced) return MC_ERR_INVALID;
     *produced = 0;
     if (!h->inflight.empty()) { h->err = "mc_process called with pipelined frames in flight"; return MC_ERR_INVALID; }
     mc_status st = mc_submit(h, in, width, height, channels, in_step, p, out, out_step);
     if (st != MC_OK) return st;
     return mc_collect(h, produced);
-}
+} catch (...) { return on_exception(h); }
 
-mc_status mc_state_dims(mc_handle* h, const char* name, int level, int* rows, int* cols, int* channels) {
+mc_status mc_state_dims(mc_handle* h, const char* name, int level, int* rows, int* cols, int* channels) try {
     if (!h || !name || !rows || !cols || !channels) return MC_ERR_INVALID;
     *rows = *cols = *channels = 0;
     StateRef r;
@@ -502,9 +550,9 @@ mc_status mc_state_dims(mc_handle* h, const char* name, int level, int* rows, in
     else if (h->t_mode == MC_MODE_PHASE) h->riesz.find_state(name, level, r);
     if (r.ptr) { *rows = r.rows; *cols = r.cols; *channels = r.channels; }
     return MC_OK;
-}
+} catch (...) { return on_exception(h); }
 
-static mc_status state_xfer(mc_handle* h, const char* name, int level, float* host, size_t n, bool get) {
+static mc_status state_xfer(mc_handle* h, const char* name, int level, float* host, size_t n, bool get) try {
     if (!h || !name || !host) return MC_ERR_INVALID;
     CK(cudaSetDevice(h->device));
     StateRef r;
@@ -522,23 +570,23 @@ static mc_status state_xfer(mc_handle* h, const char* name, int level, float* ho
         else CK(cudaMemcpy2D(d, (size_t)r.pitch * 4, hp, (size_t)r.cols * 4, (size_t)r.cols * 4, r.rows, cudaMemcpyHostToDevice));
     }
     return MC_OK;
-}
+} catch (...) { return on_exception(h); }
 
-mc_status mc_get_state(mc_handle* h, const char* name, int level, float* dst, size_t n) {
+mc_status mc_get_state(mc_handle* h, const char* name, int level, float* dst, size_t n) try {
     return state_xfer(h, name, level, dst, n, true);
-}
-mc_status mc_set_state(mc_handle* h, const char* name, int level, const float* src, size_t n) {
+} catch (...) { return on_exception(h); }
+mc_status mc_set_state(mc_handle* h, const char* name, int level, const float* src, size_t n) try {
     return state_xfer(h, name, level, const_cast<float*>(src), n, false);
-}
+} catch (...) { return on_exception(h); }
 
-mc_status mc_get_float_output(mc_handle* h, float* dst, size_t n) {
+mc_status mc_get_float_output(mc_handle* h, float* dst, size_t n) try {
     if (!h || !dst) return MC_ERR_INVALID;
     CK(cudaSetDevice(h->device));
     if (!h->float_out || n < h->float_out_floats) { h->err = "no float output kept (set keep_float_output) or buffer too small"; return MC_ERR_INVALID; }
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaMemcpy(dst, h->float_out, h->float_out_floats * sizeof(float), cudaMemcpyDeviceToHost));
     return MC_OK;
-}
+} catch (...) { return on_exception(h); }
 
 }  // extern "C"
 
@@ -554,7 +602,7 @@ extern "C" void mc_host_free(void* p) {
     if (p) cudaFreeHost(p);
 }
 
-extern "C" mc_status mc_profile_read(mc_handle* h, char* buf, size_t cap) {
+extern "C" mc_status mc_profile_read(mc_handle* h, char* buf, size_t cap) try {
     if (!h || !buf || cap == 0) return MC_ERR_INVALID;
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->stream));
@@ -580,7 +628,7 @@ extern "C" mc_status mc_profile_read(mc_handle* h, char* buf, size_t cap) {
     if (out.size() + 1 > cap) { h->err = "profile buffer too small"; return MC_ERR_INVALID; }
     std::memcpy(buf, out.c_str(), out.size() + 1);
     return MC_OK;
-}
+} catch (...) { return on_exception(h); }
 
 namespace {
 mc_status grow(mc_handle* h, uint8_t** p, size_t* cap, size_t need) {
@@ -596,7 +644,7 @@ mc_status grow(mc_handle* h, uint8_t** p, size_t* cap, size_t need) {
 // runChainOnce (ChainBuilder.cpp:19-29) = Preprocess -> Grayscale -> Magnification, fused on the device.
 extern "C" mc_status mc_chain_process(mc_handle* h, const uint8_t* in, int width, int height, int channels, size_t in_step,
                                       const mc_params* p, int grayscale, uint8_t* out, size_t out_bytes, uint8_t* original,
-                                      size_t original_bytes, mc_chain_info* info) {
+                                      size_t original_bytes, mc_chain_info* info) try {
     if (!h || !p || !info) return MC_ERR_INVALID;
     std::memset(info, 0, sizeof(*info));
     info->cur_is_input = 1; info->orig_is_input = 1;
@@ -686,4 +734,4 @@ extern "C" mc_status mc_chain_process(mc_handle* h, const uint8_t* in, int width
     }
     CK(cudaStreamSynchronize(h->stream));
     return MC_OK;
-}
+} catch (...) { return on_exception(h); }

@@ -108,17 +108,9 @@ cudaError_t launch_collapse(const Level& lf, const Level& lc, const BandSrc& fin
 
 // out = convert(input + chroma * pyrUp(pyrUp(c2) + m1)) (MagnifyCore.hpp:136-158).
 // m1.a == nullptr: no motion; c2.a == nullptr: cur_1 = m1.  C == 3 reads `lab`, C == 1 reads io.in.
-// TMA descriptors of the three tile sources of the egress kernel (option egress_tma): Lab16 planes, the stored
-// level-1 band planes and the collapsed level-2 planes
-struct EgressMaps {
-    TensorMapStorage lab, m1, c2;
-    bool valid = false, has_c2 = false;
-};
-bool make_egress_tensor_maps(EgressMaps& m, const int16_t* lab, int w, int h, int pitch16, size_t plane16, const float* m1,
-                             const Level& l1, const float* c2, const Level& l2, int planes);
 cudaError_t launch_egress(const FrameIO& io, const DeviceTables& tb, const int16_t* lab, int pitch16, size_t plane16,
                           const BandSrc& m1, const Level& l1, const BandSrc& c2, const Level& l2, float chroma,
-                          float* float_out_or_null, cudaStream_t s, const EgressMaps* maps = nullptr);
+                          float* float_out_or_null, cudaStream_t s);
 
 // The coarse end of the pyramid in one launch (option use_tail): band levels t .. t+n-1 (lv[0..n-1]) plus the plane
 // above them (lv[n]) stay resident in one CTA's shared memory per plane; see k_tail.

@@ -705,40 +705,14 @@ struct EgressArgs {
     float* fout;
 };
 
-// TMA (option egress_tma, C == 3, stored-band data flow): the three things the tile reads from HBM — the level-2
-// window, the level-1 band window and the Lab16 tile, all three channels each — are requested as bulk-tensor
-// copies by one thread at kernel entry and waited for where they are first used, so their latencies overlap each
-// other and the shared-memory phases.  The copies land the RAW windows (out-of-range elements zero-filled);
-// pyrUp's border rule (s[-1] := s[1], s[n] := s[n-1]) is applied to the window *indices* when they are read.
-template <int C, bool TMA>
-__global__ void __launch_bounds__(256) k_egress(const EgressArgs a, const __grid_constant__ CUtensorMap tm_lab,
-                                                const __grid_constant__ CUtensorMap tm_m1,
-                                                const __grid_constant__ CUtensorMap tm_c2) {
-    __shared__ __align__(128) float sC2[C][E2H][E2P];
+template <int C>
+__global__ void __launch_bounds__(256) k_egress(const EgressArgs a) {
+    __shared__ __align__(16) float sC2[C][E2H][E2P];
     __shared__ __align__(16) float sT[C][E2H][DP];    // horizontal pyrUp pass of the level-2 window rows
     __shared__ __align__(16) float sD[C][DH][DP];
-    __shared__ __align__(128) float sR[TMA ? C : 1][TMA ? DH : 1][TMA ? DP : 4];      // raw level-1 band window
-    __shared__ __align__(128) short sL[TMA ? C : 1][TMA ? TH : 1][TMA ? TW : 4];      // Lab16 tile
-    __shared__ __align__(8) uint64_t bars[3];
     const int lane = blockIdx.z;
     const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
     const int w1 = a.l1.w, h1 = a.l1.h;
-    if (TMA) {
-        if (threadIdx.x == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1); }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            if (a.m1.a && a.c2.a) {
-                mbar_expect_tx(&bars[0], C * E2H * E2P * sizeof(float));
-                tma_load_3d(&sC2[0][0][0], &tm_c2, x0 / 4 - 2, y0 / 4 - 2, lane * C, &bars[0]);
-            }
-            if (a.m1.a) {
-                mbar_expect_tx(&bars[1], C * DH * DP * sizeof(float));
-                tma_load_3d(&sR[0][0][0], &tm_m1, x0 / 2 - 1, y0 / 2 - 1, lane * C, &bars[1]);
-            }
-            mbar_expect_tx(&bars[2], C * TH * TW * sizeof(short));
-            tma_load_3d(&sL[0][0][0], &tm_lab, x0, y0, lane * C, &bars[2]);
-        }
-    }
     if (a.m1.a) {
         // cur_1 = pyrUp(cur_2) + m_1 on the tile's level-1 window; m_1 is the stored band plane, or gain_1 * (hi_1 - lo_1)
         // rebuilt from the two state planes (option band_from_state).  Position (k, j) of the window is
@@ -750,9 +724,7 @@ __global__ void __launch_bounds__(256) k_egress(const EgressArgs a, const __grid
         const bool has2 = a.c2.a != nullptr;
         const int bx2 = x0 / 4 - 2, by2 = y0 / 4 - 2;
         if (has2) {
-            if (TMA) {
-                mbar_wait(&bars[0], 0);
-            } else {
+            {
                 const size_t base2 = (size_t)(lane * C) * a.l2.plane;
                 for (int i = threadIdx.x; i < E2H * E2W; i += 256) {
                     const int k = i / E2W, j = i - k * E2W;
@@ -767,11 +739,7 @@ __global__ void __launch_bounds__(256) k_egress(const EgressArgs a, const __grid
                 const int x1 = upsrc(x0 / 2 - 1 + j, w1);
                 const int jx = (x1 >> 1) - bx2;
                 const bool odd = x1 & 1;
-                // raw window (TMA): apply the border rule to the indices; pre-mapped window (LDG path): identity
-                const int r = TMA ? upsrc(by2 + ky, a.l2.h) - by2 : ky;
-                const int cm = TMA ? upsrc(bx2 + jx - 1, a.l2.w) - bx2 : jx - 1;
-                const int c0 = TMA ? upsrc(bx2 + jx, a.l2.w) - bx2 : jx;
-                const int cp = TMA ? upsrc(bx2 + jx + 1, a.l2.w) - bx2 : jx + 1;
+                const int r = ky, cm = jx - 1, c0 = jx, cp = jx + 1;   // the window holds s[upsrc(i)]
 #pragma unroll
                 for (int ch = 0; ch < C; ++ch) {
                     const float sm = sC2[ch][r][cm], s0 = sC2[ch][r][c0], sp = sC2[ch][r][cp];
@@ -789,7 +757,6 @@ __global__ void __launch_bounds__(256) k_egress(const EgressArgs a, const __grid
         }
         const float g1 = a.m1.gain;
         const bool from_state = a.m1.b != nullptr;
-        if (TMA) mbar_wait(&bars[1], 0);
         for (int i = threadIdx.x; i < DH * DW; i += 256) {
             const int k = i / DW, j = i - k * DW;
             const int y1 = upsrc(y0 / 2 - 1 + k, h1), x1 = upsrc(x0 / 2 - 1 + j, w1);
@@ -797,12 +764,8 @@ __global__ void __launch_bounds__(256) k_egress(const EgressArgs a, const __grid
             float v[C];
 #pragma unroll
             for (int ch = 0; ch < C; ++ch) {
-                if (TMA) {
-                    v[ch] = sR[TMA ? ch : 0][TMA ? y1 - (y0 / 2 - 1) : 0][TMA ? x1 - (x0 / 2 - 1) : 0];
-                } else {
-                    v[ch] = __ldg(ph[ch] + o1);
-                    if (from_state) v[ch] = (v[ch] - __ldg(pl[ch] + o1)) * g1;
-                }
+                v[ch] = __ldg(ph[ch] + o1);
+                if (from_state) v[ch] = (v[ch] - __ldg(pl[ch] + o1)) * g1;
             }
             if (has2) {
                 const int ky = (y1 >> 1) - by2;
@@ -822,7 +785,6 @@ __global__ void __launch_bounds__(256) k_egress(const EgressArgs a, const __grid
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const int gx = x0 + 4 * tx;
     if (gx >= a.w0) return;
-    if (TMA) mbar_wait(&bars[2], 0);
     float up[C][2][4];
     if (a.m1.a) {
 #pragma unroll
@@ -851,17 +813,10 @@ __global__ void __launch_bounds__(256) k_egress(const EgressArgs a, const __grid
         uint8_t o8[4 * C];
         float of[4 * C];
         if (C == 3) {
-            short4 qL, qA, qB;
-            if (TMA) {
-                qL = *reinterpret_cast<const short4*>(&sL[0][TMA ? 2 * ty + ry : 0][TMA ? 4 * tx : 0]);
-                qA = *reinterpret_cast<const short4*>(&sL[TMA ? 1 : 0][TMA ? 2 * ty + ry : 0][TMA ? 4 * tx : 0]);
-                qB = *reinterpret_cast<const short4*>(&sL[TMA ? 2 : 0][TMA ? 2 * ty + ry : 0][TMA ? 4 * tx : 0]);
-            } else {
-                const int16_t* lp = a.lab + (size_t)(lane * 3) * a.plane16 + (size_t)gy * a.pitch16 + gx;
-                qL = __ldg(reinterpret_cast<const short4*>(lp));
-                qA = __ldg(reinterpret_cast<const short4*>(lp + a.plane16));
-                qB = __ldg(reinterpret_cast<const short4*>(lp + 2 * a.plane16));
-            }
+            const int16_t* lp = a.lab + (size_t)(lane * 3) * a.plane16 + (size_t)gy * a.pitch16 + gx;
+            const short4 qL = __ldg(reinterpret_cast<const short4*>(lp));
+            const short4 qA = __ldg(reinterpret_cast<const short4*>(lp + a.plane16));
+            const short4 qB = __ldg(reinterpret_cast<const short4*>(lp + 2 * a.plane16));
             const short vL[4] = {qL.x, qL.y, qL.z, qL.w}, vA[4] = {qA.x, qA.y, qA.z, qA.w}, vB[4] = {qB.x, qB.y, qB.z, qB.w};
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -1120,34 +1075,9 @@ cudaError_t launch_collapse(const Level& lf, const Level& lc, const BandSrc& fin
     return cudaGetLastError();
 }
 
-// {w, h, planes} map over pitched planes of `elem_bytes`-wide elements (4: f32, 2: 16-bit) with an arbitrary box
-bool make_plane_tensor_map(void* out_map, const void* base, int elem_bytes, int w, int h, int planes, size_t row_bytes,
-                           size_t plane_bytes, int box_w, int box_h, int box_d) {
-    const TensorMapEncodeFn fn = tensor_map_encoder();
-    if (!fn) return false;
-    const cuuint64_t dims[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)planes};
-    const cuuint64_t strides[2] = {(cuuint64_t)row_bytes, (cuuint64_t)plane_bytes};
-    const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)box_d};
-    const cuuint32_t estr[3] = {1u, 1u, 1u};
-    return fn(reinterpret_cast<CUtensorMap*>(out_map),
-                                          elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT16, 3,
-                                          const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
-bool make_egress_tensor_maps(EgressMaps& m, const int16_t* lab, int w, int h, int pitch16, size_t plane16, const float* m1,
-                             const Level& l1, const float* c2, const Level& l2, int planes) {
-    m.valid = make_plane_tensor_map(&m.lab, lab, 2, w, h, planes, (size_t)pitch16 * 2, plane16 * 2, TW, TH, 3) &&
-              make_plane_tensor_map(&m.m1, m1, 4, l1.w, l1.h, planes, (size_t)l1.pitch * 4, l1.plane * 4, DP, DH, 3) &&
-              (!c2 || make_plane_tensor_map(&m.c2, c2, 4, l2.w, l2.h, planes, (size_t)l2.pitch * 4, l2.plane * 4, E2P, E2H, 3));
-    m.has_c2 = c2 != nullptr;
-    return m.valid;
-}
-
 cudaError_t launch_egress(const FrameIO& io, const DeviceTables& tb, const int16_t* lab, int pitch16, size_t plane16,
                           const BandSrc& m1, const Level& l1, const BandSrc& c2, const Level& l2, float chroma,
-                          float* fout, cudaStream_t s, const EgressMaps* maps) {
+                          float* fout, cudaStream_t s) {
     EgressArgs a;
     a.in = io.in; a.in_step = io.in_step; a.in_lane_stride = io.in_lane_stride;
     a.lab = lab; a.pitch16 = pitch16; a.plane16 = plane16;
@@ -1156,14 +1086,8 @@ cudaError_t launch_egress(const FrameIO& io, const DeviceTables& tb, const int16
     a.gtab = tb.inv_gamma; a.coeffs = tb.inv_coeffs;
     a.m1 = m1; a.l1 = l1; a.c2 = c2; a.l2 = l2; a.chroma = chroma; a.fout = fout;
     dim3 grid(cdiv(io.w, TW), cdiv(io.h, TH), io.lanes);
-    static const CUtensorMap dummy{};
-    // TMA variant: 3 channels, stored-band data flow, maps built for exactly these buffers
-    const bool tma = maps && maps->valid && io.channels == 3 && !m1.b && !c2.b && (!c2.a || maps->has_c2) && (m1.a || !c2.a);
-    if (tma) k_egress<3, true><<<grid, 256, 0, s>>>(a, *reinterpret_cast<const CUtensorMap*>(&maps->lab),
-                                                     *reinterpret_cast<const CUtensorMap*>(&maps->m1),
-                                                     *reinterpret_cast<const CUtensorMap*>(&maps->c2));
-    else if (io.channels == 3) k_egress<3, false><<<grid, 256, 0, s>>>(a, dummy, dummy, dummy);
-    else k_egress<1, false><<<grid, 256, 0, s>>>(a, dummy, dummy, dummy);
+    if (io.channels == 3) k_egress<3><<<grid, 256, 0, s>>>(a);
+    else k_egress<1><<<grid, 256, 0, s>>>(a);
     return cudaGetLastError();
 }
 

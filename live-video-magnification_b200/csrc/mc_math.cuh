@@ -224,7 +224,12 @@ __device__ __forceinline__ void lab_to_bgr_fast(float L, float a, float b, const
     float vg = k.c[3] * X + k.c[4] * Y + k.c[5] * Z;
     float vr = k.c[6] * X + k.c[7] * Y + k.c[8] * Z;
     if (NAN_AS_OPENCV) {
-        vb = fmaxf(fminf(vb, 1.0f), 0.0f); vg = fmaxf(fminf(vg, 1.0f), 0.0f); vr = fmaxf(fminf(vr, 1.0f), 0.0f);
+        // NOT fmaxf(fminf(v, 1), 0): ptxas folds that pair into the producing FFMA as .SAT, and .SAT turns NaN into 0
+        // (black) where OpenCV's max(min(v,1),0) gives 1 (white).  The explicit NaN select survives the fold
+        // (round-1 GPUTEST failure; tools/check_sass.py asserts the FSETP.NAN/FSEL pair is in k_riesz_egress).
+        vb = (vb != vb) ? 1.0f : __saturatef(vb);
+        vg = (vg != vg) ? 1.0f : __saturatef(vg);
+        vr = (vr != vr) ? 1.0f : __saturatef(vr);
     } else {
         vb = __saturatef(vb); vg = __saturatef(vg); vr = __saturatef(vr);
     }

@@ -4,6 +4,7 @@
 #pragma once
 #include <cufft.h>
 
+#include <map>
 #include <string>
 #include <vector>
 
@@ -40,8 +41,6 @@ struct ModeCtx {
     bool use_tail;          // levels >= MotionMode::tail_start run in the single fused tail kernel (option "use_tail", default off
                             // until measured on the B200)
     bool ingest_compact;    // ingest: each LUT gather instruction serves 32 adjacent pixels (option "ingest_compact", default off
-                            // until measured on the B200)
-    bool egress_tma;        // egress requests its three tile sources by TMA at kernel entry (option "egress_tma", default off
                             // until measured on the B200)
     bool band_from_state;   // synthesis rebuilds gain*(hi-lo) from the state planes instead of reading a stored band
                             // (option "band_from_state", default off: measured no faster on B200)
@@ -81,6 +80,7 @@ struct DeviceArena {
     std::vector<void*> blocks;
     cudaError_t alloc(float** p, size_t floats);
     cudaError_t alloc_bytes(void** p, size_t bytes);
+    void free_block(void* p);   // returns one block early (buffers replaced when a ring grows)
     void release();
 };
 
@@ -100,9 +100,9 @@ struct MotionMode {
 
     std::vector<TensorMapStorage> tmaps;   // per level: TMA descriptor of G[l] (tmap_valid[l] != 0)
     int tail_start = 0;                    // first level of the fused tail kernel (0: none fits), option use_tail
-    EgressMaps egress_maps;                // TMA descriptors of the egress kernel's tile sources (option egress_tma)
     std::vector<TensorMapStorage> tmaps_hi, tmaps_lo;   // ... and of the state planes (64 x 32 tiles, option prefetch_state)
     std::vector<char> tmap_valid;
+    std::vector<float> gains;              // per-level gains of the current frame (member: no per-frame allocation)
 
     void reset();
     mc_status process(const ModeCtx& ctx, const FrameIO& io, const mc_params& p, int levels, int* produced);
@@ -127,11 +127,13 @@ struct ColorMode {
     cufftComplex* spec = nullptr;
     float* minmax = nullptr;    // device scalars
     int small_rows = 0;         // pixels of the small level
-    int ring_cap = 0;           // physical slots allocated (>= getOptimalBufferSize(int(framerate)))
-    void* mask_dev = nullptr;
-    int mask_cap = 0;
-    cufftHandle plan_r2c = 0, plan_c2r = 0;
-    int plan_n = 0;
+    int ring_cap = 0;           // physical slots allocated
+    int ring_mod = 0;           // logical ring size (<= ring_cap): max(getOptimalBufferSize(int(framerate)), window length)
+    struct FftPlans { cufftHandle r2c = 0, c2r = 0; size_t work_bytes = 0; void* bound = nullptr; };
+    std::map<int, FftPlans> plans;   // per DFT length (the window length: 2 ... cap during warm-up), for plan_signals signals
+    size_t plan_signals = 0;
+    void* fft_work = nullptr;        // one work area shared by all cached plans (they run back to back on one stream)
+    size_t fft_work_bytes = 0;
     DeviceArena arena;
 
     void reset();

@@ -19,6 +19,14 @@ cudaError_t DeviceArena::alloc_bytes(void** p, size_t bytes) {
     if (e == cudaSuccess) blocks.push_back(*p);
     return e;
 }
+void DeviceArena::free_block(void* p) {
+    for (size_t i = 0; i < blocks.size(); ++i)
+        if (blocks[i] == p) {
+            cudaFree(p);
+            blocks.erase(blocks.begin() + (long)i);
+            return;
+        }
+}
 void DeviceArena::release() {
     for (void* b : blocks) cudaFree(b);
     blocks.clear();
@@ -84,11 +92,6 @@ mc_status MotionMode::allocate(const ModeCtx& ctx, const FrameIO& io, int nlevel
     tail_start = 0;
     for (int l = 2; l <= levels - 2 && !tail_start; ++l)
         if (levels - l <= kTailMaxLevels && tail_smem_bytes(&lv[(size_t)l], levels - l) <= kTailSmemBudget) tail_start = l;
-    // TMA descriptors of the egress kernel's three tile sources (option egress_tma; 3 channels, stored band)
-    egress_maps = EgressMaps{};
-    if (channels == 3 && !from_state && levels >= 2 && M[1])
-        make_egress_tensor_maps(egress_maps, lab16, w, h, pitch16, plane16, M[1], lv[1], levels >= 3 ? M[2] : nullptr, lv[2 <= levels ? 2 : 0],
-                                (int)planes);
     allocated = true;
     return MC_OK;
 }
@@ -101,7 +104,6 @@ mc_status MotionMode::process(const ModeCtx& ctx, const FrameIO& io, const mc_pa
     const int planes = lanes * channels;
     const bool first = empty;  // MagnifyCore.hpp:98
 
-    std::vector<float> gains;
     motion_gains(p.amplification, p.coWavelength, levels, w, h, gains);
     double c_lo = p.coLow, c_hi = p.coHigh;
     if (c_lo == 0) c_lo = 0.01;  // TemporalFilter.cpp:11-12
@@ -188,7 +190,7 @@ mc_status MotionMode::process(const ModeCtx& ctx, const FrameIO& io, const mc_pa
     const Level& l1 = lv[levels >= 1 ? 1 : 0];
     const Level& l2 = lv[levels >= 2 ? 2 : 0];
     LAUNCH("egress", 0, launch_egress(io, *ctx.tables, lab16, pitch16, plane16, m1, l1, c2, l2, (float)p.chromAttenuation, ctx.float_out,
-                                      ctx.stream, ctx.egress_tma && ctx.use_tma ? &egress_maps : nullptr));
+                                      ctx.stream));
     empty = false;
     *produced = 1;
     return MC_OK;

@@ -19,7 +19,7 @@ def pytest_configure(config):
 
 
 def pytest_collection_modifyitems(config, items):
-    """Kernel options that ship off (prefetch_state, egress_tma, use_tail) are verified on the emulation only until
+    """Kernel options that ship off (prefetch_state, use_tail, ingest_compact) are verified on the emulation only until
     their first B200 measurement; their tests do not gate the default GPU suite (`-x` would stop it at the first
     surprise) — run them on hardware with MC_EXPERIMENTAL=1."""
     if os.environ.get("MC_EMU") == "1" or os.environ.get("MC_EXPERIMENTAL") == "1":

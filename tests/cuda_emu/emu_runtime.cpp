@@ -543,6 +543,24 @@ cufftResult cufftPlanMany(cufftHandle* plan, int rank, int* n, int*, int istride
     *plan = (cufftHandle)g_plans.size() - 1;
     return CUFFT_SUCCESS;
 }
+cufftResult cufftCreate(cufftHandle* plan) {
+    g_plans.push_back(Plan{0, 0, 0, 0, 0, 0, CUFFT_R2C, false, nullptr});
+    *plan = (cufftHandle)g_plans.size() - 1;
+    return CUFFT_SUCCESS;
+}
+cufftResult cufftSetAutoAllocation(cufftHandle p, int) { return (p <= 0 || (size_t)p >= g_plans.size()) ? CUFFT_INVALID_PLAN : CUFFT_SUCCESS; }
+cufftResult cufftMakePlanMany(cufftHandle p, int rank, int* n, int*, int istride, int idist, int*, int ostride, int odist,
+                              cufftType type, int batch, size_t* workSize) {
+    if (p <= 0 || (size_t)p >= g_plans.size()) return CUFFT_INVALID_PLAN;
+    if (rank != 1 || n[0] < 1 || batch < 1 || (type != CUFFT_R2C && type != CUFFT_C2R)) return CUFFT_INVALID_VALUE;
+    g_plans[(size_t)p] = Plan{n[0], istride, idist, ostride, odist, batch, type, true, nullptr};
+    if (workSize) *workSize = 256;   // a token amount, so the caller's shared-work-area path runs
+    return CUFFT_SUCCESS;
+}
+cufftResult cufftSetWorkArea(cufftHandle p, void* w) {
+    if (p <= 0 || (size_t)p >= g_plans.size()) return CUFFT_INVALID_PLAN;
+    return w ? CUFFT_SUCCESS : CUFFT_INVALID_VALUE;
+}
 cufftResult cufftSetStream(cufftHandle p, cudaStream_t s) {
     if (p <= 0 || (size_t)p >= g_plans.size()) return CUFFT_INVALID_PLAN;
     g_plans[(size_t)p].stream = s;

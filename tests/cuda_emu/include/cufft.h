@@ -11,6 +11,12 @@ enum cufftType { CUFFT_R2C = 0x2a, CUFFT_C2R = 0x2c, CUFFT_C2C = 0x29 };
 
 cufftResult cufftPlanMany(cufftHandle* plan, int rank, int* n, int* inembed, int istride, int idist, int* onembed, int ostride,
                           int odist, cufftType type, int batch);
+// plan objects with a caller-owned work area (the product shares one work area between its cached plans)
+cufftResult cufftCreate(cufftHandle* plan);
+cufftResult cufftSetAutoAllocation(cufftHandle plan, int autoAllocate);
+cufftResult cufftMakePlanMany(cufftHandle plan, int rank, int* n, int* inembed, int istride, int idist, int* onembed, int ostride,
+                              int odist, cufftType type, int batch, size_t* workSize);
+cufftResult cufftSetWorkArea(cufftHandle plan, void* workArea);
 cufftResult cufftSetStream(cufftHandle plan, cudaStream_t s);
 cufftResult cufftExecR2C(cufftHandle plan, cufftReal* in, cufftComplex* out);
 cufftResult cufftExecC2R(cufftHandle plan, cufftComplex* in, cufftReal* out);

@@ -96,3 +96,60 @@ def test_emulation_selftest(env):
                        check=True)
     r = subprocess.run([exe], env={**os.environ, **env}, capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and "selftest: ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_exception_inside_a_frame_is_contained_and_resets_state(emu):
+    """A C++ exception thrown while a frame is being processed (std::bad_alloc injected at the top of the device-side
+    body) comes back as MC_ERR_INTERNAL, drops the temporal state (the recovery contract of
+    ProcessingChain.cpp:50-62) and leaves the handle usable: the next frames equal a fresh stream's."""
+    import ctypes as C
+    lib = capi.lib()
+    lib.mc_debug_inject_exception.argtypes = [C.c_int]
+    lib.mc_debug_inject_exception.restype = None
+    cfg, ocfg = make_cfgs(O.MODE_LAPLACE, 20, 50.0, 0.4, 3.0, 0, 3)
+    proc = L.MagnificationProcessor(0)
+    for t in range(3):
+        proc.process_image(synth_frame(t, 80, 60, 3), cfg)
+    lib.mc_debug_inject_exception(1)
+    with pytest.raises(L.MagcoreError) as e:
+        proc.process_image(synth_frame(3, 80, 60, 3), cfg)
+    assert e.value.status == capi.MC_ERR_INTERNAL and "bad_alloc" in str(e.value)
+    oproc = O.MagnificationProcessor()                       # the stream restarts from scratch after the failure
+    for t in range(4, 7):
+        f = synth_frame(t, 80, 60, 3)
+        produced, out = proc.process_image(f, cfg)
+        oprod, oout = oproc.process(f, ocfg)
+        assert produced == oprod and int(u8_diff(out, oout).max()) <= 1
+    proc.close()
+
+
+def test_color_many_lanes_and_frame_rate_sweep(emu):
+    """(1) the per-lane min/max scratch must be initialised for EVERY lane (lanes > 64 used to read
+    uninitialised slots); (2) sweeping the frame rate up and down re-lays the ring out once per change (no per-frame
+    compaction, no leaked buffers) and still matches the reference's window semantics."""
+    lanes, w, h = 70, 24, 20
+    cfg, ocfg = make_cfgs(O.MODE_COLOR, 60, 0.0, 0.8, 1.2, 0, 1, 8.0)
+    proc = L.MagnificationProcessor(0, lanes=lanes)
+    oprocs = {k: O.MagnificationProcessor() for k in (0, 63, 64, 69)}
+    for t in range(6):
+        clip = np.stack([np.roll(synth_frame(t, w, h, 3, fps=8.0), (k, 2 * k), axis=(0, 1)) for k in range(lanes)])
+        produced, out = proc.process_image(clip, cfg)
+        for k, op in oprocs.items():
+            oprod, oout = op.process(clip[k], ocfg)
+            assert produced == oprod
+            if produced:
+                assert int(u8_diff(out[k], oout).max()) <= 1, (t, k)
+    proc.close()
+    proc, oproc = L.MagnificationProcessor(0), O.MagnificationProcessor()
+    t = 0
+    for fps in (8.0, 30.0, 8.0, 4.0, 16.0):          # caps 16 -> 64 -> 16 -> 8 -> 32, partly and fully filled windows
+        cfg, ocfg = make_cfgs(O.MODE_COLOR, 60, 0.0, 0.8, 1.2, 0, 1, fps)
+        for _ in range(11):
+            f = synth_frame(t, 40, 30, 3, fps=8.0)
+            produced, out = proc.process_image(f, cfg)
+            oprod, oout = oproc.process(f, ocfg)
+            assert produced == oprod, (fps, t)
+            if produced:
+                assert int(u8_diff(out, oout).max()) <= 1, (fps, t)
+            t += 1
+    proc.close()

@@ -349,22 +349,6 @@ def test_prefetch_state_option_equals_default():
 
 
 @pytest.mark.experimental
-def test_egress_tma_option_equals_default():
-    """Option egress_tma (Lab16 tile, level-1 band window and level-2 window fetched as TMA bulk copies, border rule
-    applied to window indices) must not change a single bit — interior tiles, ragged borders, 2 and 3 levels (no /
-    top-band level-2 window) and the first frame (no motion) included."""
-    for (w, h, lv) in [(640, 480, 4), (333, 251, 5), (131, 75, 3), (200, 120, 2), (64, 48, 6)]:
-        cfg, _ = make_cfgs(O.MODE_LAPLACE, 20, 50.0, 0.4, 3.0, 30, lv)
-        a, b = L.MagnificationProcessor(0), L.MagnificationProcessor(0)
-        b.set_option("egress_tma", 1)
-        for t in range(4):
-            f = synth_frame(t, w, h, 3)
-            _, oa = a.process_image(f, cfg)
-            _, ob = b.process_image(f, cfg)
-            assert np.array_equal(oa, ob), (w, h, lv, t)
-
-
-@pytest.mark.experimental
 @pytest.mark.parametrize("w,h,c,levels", [(640, 480, 3, 4), (322, 241, 3, 5), (333, 251, 1, 6), (1920, 1080, 3, 6), (200, 120, 3, 3)])
 def test_fused_tail_option(w, h, c, levels):
     """Option use_tail: the coarse levels (all whose planes fit one CTA's shared memory) run in ONE kernel instead of
@@ -397,8 +381,8 @@ def test_fused_tail_option(w, h, c, levels):
 
 
 @pytest.mark.experimental
-@pytest.mark.parametrize("opts", [("use_tail", "prefetch_state", "egress_tma", "ingest_compact"), ("use_tail", "band_from_state", "prefetch_state"),
-                                  ("use_tail", "faithful_level0"), ("prefetch_state", "egress_tma")])
+@pytest.mark.parametrize("opts", [("use_tail", "prefetch_state", "ingest_compact"), ("use_tail", "band_from_state", "prefetch_state"),
+                                  ("use_tail", "faithful_level0"), ("prefetch_state", "ingest_compact")])
 def test_option_combinations_agree_with_default(opts):
     """The A/B options compose: any combination gives the default path's frames (bit-identical without the fused
     tail, to float rounding with it), over the first frame, ragged borders and a parameter change."""

@@ -30,6 +30,7 @@ def test_library_exports_every_declared_symbol(built):
     assert not missing, missing
     assert declared == set(capi.SIGNATURES), declared ^ set(capi.SIGNATURES)
     assert lib.mc_abi_version() == 2
+    assert hasattr(lib, "mc_debug_inject_exception")   # test hook, deliberately not in the public header
 
 
 def test_no_cpu_fallback_without_gpu(built):
@@ -188,3 +189,36 @@ def test_front_stage_arithmetic_is_bit_exact_with_cv2(hc):
         img = np.zeros((rows, cols), np.uint8)
         _, cropped = O.preprocess(img, cfg)
         assert (out[2], out[3]) == (cropped.shape[1], cropped.shape[0]), (cols, rows, list(out))
+
+
+def test_c_abi_is_an_exception_firewall(built):
+    """include/magcore_b200.h: "no exceptions cross this boundary".  The test hook mc_debug_inject_exception(n) makes
+    the n-th guarded entry on this thread throw std::bad_alloc from INSIDE the body; the call must come back with
+    MC_ERR_INTERNAL and a message (not std::terminate the process), and the library must keep working afterwards.
+    (Error convention of the chain above the adapter: reference src/processing/ProcessingChain.cpp:50-62.)"""
+    lib = capi.lib()
+    raw = C.CDLL(built[0])
+    raw.mc_debug_inject_exception.argtypes = [C.c_int]
+    raw.mc_debug_inject_exception.restype = None
+    a, b = (C.c_double * 3)(), (C.c_double * 3)()
+    raw.mc_debug_inject_exception(1)
+    assert lib.mc_butterworth(2, 0.2, a, b) == capi.MC_ERR_INTERNAL
+    assert b"bad_alloc" in lib.mc_last_error(None)
+    assert lib.mc_butterworth(2, 0.2, a, b) == capi.MC_OK and abs(a[0] - 1.0) < 1e-15     # disarmed, still works
+    p = capi.McParams()
+    lib.mc_params_from_ui(C.byref(p), 0, 20, 50.0, 0.4, 3.0, 0, 4, 30.0)
+    g = (C.c_float * 5)()
+    raw.mc_debug_inject_exception(2)                                                       # the SECOND entry throws
+    assert lib.mc_motion_gains(C.byref(p), 4, 640, 480, g) == capi.MC_OK
+    assert lib.mc_motion_gains(C.byref(p), 4, 640, 480, g) == capi.MC_ERR_INTERNAL
+    assert lib.mc_motion_gains(C.byref(p), 4, 640, 480, g) == capi.MC_OK
+    # a throw inside mc_create_lanes must not leak through either (no device here: the NO_DEVICE return comes first,
+    # on a GPU box the injected throw is caught)
+    h = C.c_void_p()
+    raw.mc_debug_inject_exception(1)
+    st = lib.mc_create_lanes(0, 1, C.byref(h))
+    assert st in (capi.MC_ERR_NO_DEVICE, capi.MC_ERR_INTERNAL) and not h.value
+    raw.mc_debug_inject_exception(0)
+    # argument validation added with it: lane count bounds (grid.z = lanes * channels)
+    assert lib.mc_create_lanes(0, 0, C.byref(h)) == capi.MC_ERR_INVALID
+    assert lib.mc_create_lanes(0, capi.MC_MAX_LANES + 1, C.byref(h)) == capi.MC_ERR_INVALID

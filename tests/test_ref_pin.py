@@ -7,6 +7,8 @@ temporal state (EMA planes, rolling window, Riesz pyramids and IIR outputs).  CP
 
 Skipped only when the module is neither prebuilt nor buildable (no /root/reference and no oracle/_ref/*.so).
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -15,6 +17,8 @@ from oracle import livim_oracle as O
 from oracle import livim_ref
 
 R = livim_ref.load()
+if R is None and os.environ.get("MC_REQUIRE_REF") == "1":
+    raise RuntimeError("MC_REQUIRE_REF=1 but oracle/_ref/_livim_ref is missing")
 pytestmark = pytest.mark.skipif(R is None, reason="oracle/_ref/_livim_ref is not built and /root/reference is absent")
 
 
@@ -238,7 +242,7 @@ def test_dropin_chain_builds_against_real_reference_headers_and_has_no_cpu_fallb
     Frame.hpp.  Without a GPU constructing it must fail loudly: mc_create reports no device, the adapter throws."""
     import torch
     if torch.cuda.is_available():
-        pytest.skip("GPU present: covered by tests/test_gpu_zz_vs_reference.py::test_dropin_chain_on_gpu")
+        pytest.skip("GPU present: covered by tests/test_gpu_vs_reference.py::test_dropin_chain_on_gpu")
     R.set_magcore_library(built[0])
     with pytest.raises(RuntimeError, match="magcore_b200"):
         R.DropInChain(0)

@@ -142,7 +142,7 @@ def main():
         proc = L.MagnificationProcessor(0)
         opts = []
         if args.options:
-            opts = [k for k in ("prefetch_state", "egress_tma", "use_tail", "ingest_compact", "band_from_state", "faithful_level0", "use_tma")
+            opts = [k for k in ("prefetch_state", "use_tail", "ingest_compact", "band_from_state", "faithful_level0", "use_tma")
                     if rng.random() < 0.4]
             for k in opts:
                 proc.set_option(k, 0 if k == "use_tma" else 1)

@@ -5,7 +5,7 @@ the blocking host API.  Prints one JSON line.
 
     python tests/tools/quick_gpu_probe.py                 # parity + one table (PROBE_LANES, default 8)
     python tests/tools/quick_gpu_probe.py --ab 8,32       # A/B of the kernel options at those lane counts:
-                                                    # default | prefetch_state | egress_tma | use_tail | ingest_compact | all four | band_from_state | ...
+                                                    # default | prefetch_state | use_tail | ingest_compact | all four | band_from_state | ...
 """
 import json
 import os
@@ -28,7 +28,7 @@ def main():
     out = {}
     pw, ph = int(os.environ.get("PROBE_W", "1920")), int(os.environ.get("PROBE_H", "1080"))
     R = livim_ref.load()
-    for (w, h, levels, n) in ((320, 240, 4, 6), (pw, ph, 6, 3)):
+    for (w, h, levels, n) in (() if os.environ.get("PROBE_SKIP_PARITY") == "1" else ((320, 240, 4, 6), (pw, ph, 6, 3))):
         cfg, ocfg = make_cfgs(O.MODE_LAPLACE, 20, 50.0, 0.4, 3.0, 30, levels)
         proc = L.MagnificationProcessor(0)
         ref = R.Processor() if R is not None else O.MagnificationProcessor()
@@ -84,12 +84,22 @@ def main():
 
     if "--ab" in sys.argv:
         lane_list = [int(x) for x in sys.argv[sys.argv.index("--ab") + 1].split(",")]
-        out["ab"] = [table_for(n, o) for n in lane_list
-                     for o in ({}, {"prefetch_state": 1}, {"egress_tma": 1}, {"use_tail": 1}, {"ingest_compact": 1},
-                               {"prefetch_state": 1, "egress_tma": 1, "use_tail": 1, "ingest_compact": 1},
-                               {"band_from_state": 1}, {"prefetch_state": 1, "band_from_state": 1})]
+        # every variant in its own process: a kernel fault poisons the CUDA context of the process it happens in
+        import subprocess
+        variants = ({}, {"prefetch_state": 1}, {"use_tail": 1}, {"ingest_compact": 1},
+                    {"prefetch_state": 1, "use_tail": 1, "ingest_compact": 1}, {"band_from_state": 1},
+                    {"prefetch_state": 1, "band_from_state": 1})
+        out["ab"] = []
+        for n in lane_list:
+            for o in variants:
+                env = dict(os.environ, PROBE_LANES=str(n), PROBE_OPTIONS=json.dumps(o), PROBE_SKIP_PARITY="1")
+                r = subprocess.run([sys.executable, os.path.abspath(__file__)], env=env, capture_output=True, text=True, timeout=120)
+                try:
+                    out["ab"].append(json.loads(r.stdout.strip().splitlines()[-1]))
+                except Exception:
+                    out["ab"].append({"lanes": n, "options": o, "failed": (r.stderr or r.stdout)[-400:]})
     else:
-        out.update(table_for(int(os.environ.get("PROBE_LANES", "8")), {}))
+        out.update(table_for(int(os.environ.get("PROBE_LANES", "8")), json.loads(os.environ.get("PROBE_OPTIONS", "{}"))))
     out["seconds"] = round(time.time() - t00, 1)
     print(json.dumps(out))
 
