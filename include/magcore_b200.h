@@ -161,21 +161,17 @@ void* mc_stream(mc_handle* h);
  *   "profile_kernels" (default 0): see mc_profile_read
  *   "use_tma" (default 1): stage the fused level kernel's tiles with TMA (cp.async.bulk.tensor); 0 selects
  *        the 128-bit LDG staging path (same results; kept for A/B measurements)
- *   "prefetch_state" (default 0; needs use_tma): the fused level kernel requests the tile's two state planes as TMA
+ *   "prefetch_state" (default 1; needs use_tma): the fused level kernel requests the tile's two state planes as TMA
  *        bulk copies at kernel entry, together with its input window, instead of loading them in its last phase
- *        (same results; for A/B measurements — the kernel is latency-bound)
- *   "use_tail" (default 0): Laplace — the coarse pyramid levels whose planes together fit one CTA's shared memory
- *        (levels >= 3 at 1080p) are analysed, filtered and collapsed by one kernel launch instead of one launch per
- *        level and direction (results within float rounding of the per-level kernels; for A/B measurements)
- *   "ingest_compact" (default 0): the fused BGR->Lab ingest routes each row through shared memory so that one gather
- *        instruction of the exact OpenCV Lab LUT serves 32 adjacent pixels instead of 32 pixels four columns apart
- *        (same results; fewer L1 wavefronts on coherent content; for A/B measurements)
+ *        (same results; measured on B200: level[1] 235 -> 205 us per 32-lane launch; 0 kept for A/B measurements)
+ *   "ingest_warps" (default 1): warps per CTA (1, 2 or 4) of the fused BGR->Lab ingest kernel (same results; A/B)
  *   "analysis_only" (default 0): Laplace and Phase — frames after the first update the temporal state (EMA planes;
  *        Riesz pyramids, phase accumulators and Butterworth registers) but skip synthesis and egress and report
  *        *produced = 0; the cheap first pass of temporal sharding
- *   "band_from_state" (default 0): Laplace synthesis rebuilds each amplified band gain*(hi-lo) from the two
+ *   "band_from_state" (default 1): Laplace synthesis rebuilds each amplified band gain*(hi-lo) from the two
  *        state planes instead of reading a band plane stored by the level kernel (same results; takes 4 B/px off
- *        the level kernel's interface and adds them to the collapse / egress kernels; kept for A/B measurements) */
+ *        the level kernel's interface and adds them to the collapse / egress kernels; measured on B200 together
+ *        with prefetch_state: level[1] 205 -> 177 us, egress +8 us, step -1.6 %; 0 kept for A/B measurements) */
 mc_status mc_set_option(mc_handle* h, const char* key, int value);
 
 /* Test-only access to temporal state planes as dense f32 [lanes][channels][rows][cols].

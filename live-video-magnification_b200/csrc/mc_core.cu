@@ -46,7 +46,8 @@ struct mc_handle {
     float t_rx = 0.f, t_ry = 0.f, t_rw = 1.f, t_rh = 1.f;
 
     // options
-    bool faithful0 = false, keep_float = false, profile = false, use_tma = true, prefetch_state = false, use_tail = false, ingest_compact = false, band_from_state = false, analysis_only = false;
+    bool faithful0 = false, keep_float = false, profile = false, use_tma = true, prefetch_state = true, band_from_state = true, analysis_only = false;
+    int ingest_warps = 1;
     Profiler prof;
     int depth = 3;
 
@@ -228,7 +229,7 @@ mc_status process_device_impl(mc_handle* h, const uint8_t* d_in, int w, int hh, 
         fout = h->float_out;
     }
 
-    ModeCtx ctx{h->stream, &h->tables, &h->launches, &h->err, h->faithful0, fout, h->profile ? &h->prof : nullptr, h->use_tma, h->prefetch_state, h->use_tail, h->ingest_compact, h->band_from_state, h->analysis_only};
+    ModeCtx ctx{h->stream, &h->tables, &h->launches, &h->err, h->faithful0, fout, h->profile ? &h->prof : nullptr, h->use_tma, h->prefetch_state, h->ingest_warps, h->band_from_state, h->analysis_only};
     mc_status st = MC_OK;
     switch (p->mode) {
         case MC_MODE_LAPLACE: st = h->motion.process(ctx, io, *p, levels, produced); break;
@@ -360,15 +361,15 @@ mc_status mc_create_lanes(int device, int lanes, mc_handle** out) try {
     if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("stream", e);
     if ((e = cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking)) != cudaSuccess) return fail("stream", e);
     if ((e = cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking)) != cudaSuccess) return fail("stream", e);
-    std::vector<LabLutEntry> lut;
-    build_lab_lut_packed(lut);
+    std::vector<LabLutCell> lut;
+    build_lab_lut_cells(lut);
     if (lut.empty()) { g_create_error = "embedded Lab LUT missing"; mc_destroy(h); return MC_ERR_INVALID; }
     std::vector<float4> gam;
     build_inv_gamma_spline(gam);
     build_lab_inv_coeffs(h->tables.inv_coeffs);
-    if ((e = cudaMalloc((void**)&h->tables.lab_lut, lut.size() * sizeof(LabLutEntry))) != cudaSuccess) return fail("cudaMalloc lut", e);
+    if ((e = cudaMalloc((void**)&h->tables.lab_lut, lut.size() * sizeof(LabLutCell))) != cudaSuccess) return fail("cudaMalloc lut", e);
     if ((e = cudaMalloc((void**)&h->tables.inv_gamma, gam.size() * sizeof(float4))) != cudaSuccess) return fail("cudaMalloc gamma", e);
-    if ((e = cudaMemcpy(h->tables.lab_lut, lut.data(), lut.size() * sizeof(LabLutEntry), cudaMemcpyHostToDevice)) != cudaSuccess) return fail("copy lut", e);
+    if ((e = cudaMemcpy(h->tables.lab_lut, lut.data(), lut.size() * sizeof(LabLutCell), cudaMemcpyHostToDevice)) != cudaSuccess) return fail("copy lut", e);
     if ((e = cudaMemcpy(h->tables.inv_gamma, gam.data(), gam.size() * sizeof(float4), cudaMemcpyHostToDevice)) != cudaSuccess) return fail("copy gamma", e);
     h->motion.lanes = h->color.lanes = h->riesz.lanes = lanes;
     *out = h;
@@ -419,8 +420,7 @@ mc_status mc_set_option(mc_handle* h, const char* key, int value) try {
     if (!std::strcmp(key, "profile_kernels")) { h->profile = value != 0; return MC_OK; }
     if (!std::strcmp(key, "use_tma")) { h->use_tma = value != 0; return MC_OK; }
     if (!std::strcmp(key, "prefetch_state")) { h->prefetch_state = value != 0; return MC_OK; }
-    if (!std::strcmp(key, "use_tail")) { h->use_tail = value != 0; return MC_OK; }
-    if (!std::strcmp(key, "ingest_compact")) { h->ingest_compact = value != 0; return MC_OK; }
+    if (!std::strcmp(key, "ingest_warps")) { h->ingest_warps = value; return MC_OK; }
     if (!std::strcmp(key, "band_from_state")) { h->band_from_state = value != 0; return MC_OK; }
     if (!std::strcmp(key, "analysis_only")) { h->analysis_only = value != 0; return MC_OK; }
     if (!std::strcmp(key, "pipeline_depth")) {

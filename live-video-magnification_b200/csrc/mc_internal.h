@@ -28,13 +28,13 @@ inline Level make_level(int w, int h) {
 
 // Device constant tables shared by every handle on a device (built once per device).
 struct DeviceTables {
-    LabLutEntry* lab_lut = nullptr;   // [33][33][33]
+    LabLutCell* lab_lut = nullptr;   // [34][33][33] cells (mc_math.cuh)
     float4* inv_gamma = nullptr;      // [1024] spline coefficients {f, b, c, d}
     LabInvCoeffs inv_coeffs{};
 };
 
 // mc_tables.cpp ------------------------------------------------------------------------------
-void build_lab_lut_packed(std::vector<LabLutEntry>& out);          // from the embedded int16 table
+void build_lab_lut_cells(std::vector<LabLutCell>& out);          // from the embedded int16 table
 void build_inv_gamma_spline(std::vector<float4>& out);             // OpenCV sRGBInvGammaTab
 void build_lab_inv_coeffs(LabInvCoeffs& out);
 int calculate_max_levels(int w, int h);
@@ -63,7 +63,7 @@ cudaError_t launch_lab16(const FrameIO& io, const DeviceTables& tb, int16_t* lab
 
 // fused ingest of the production path: u8 BGR -> Lab16 planes + G1 = pyrDown(Lab) (MagnifyCore.hpp:87-96, level 0)
 cudaError_t launch_ingest_lab(const FrameIO& io, const DeviceTables& tb, int16_t* lab, int pitch16, size_t plane16,
-                              float* g1, const Level& l1, cudaStream_t s, bool compact = false);
+                              float* g1, const Level& l1, cudaStream_t s, int warps_per_cta = 1);
 
 struct LevelArgs {
     int in_kind = 0;           // 0: f32 planes, 1: Lab int16 planes, 2: u8 gray frame
@@ -111,26 +111,6 @@ cudaError_t launch_collapse(const Level& lf, const Level& lc, const BandSrc& fin
 cudaError_t launch_egress(const FrameIO& io, const DeviceTables& tb, const int16_t* lab, int pitch16, size_t plane16,
                           const BandSrc& m1, const Level& l1, const BandSrc& c2, const Level& l2, float chroma,
                           float* float_out_or_null, cudaStream_t s);
-
-// The coarse end of the pyramid in one launch (option use_tail): band levels t .. t+n-1 (lv[0..n-1]) plus the plane
-// above them (lv[n]) stay resident in one CTA's shared memory per plane; see k_tail.
-constexpr int kTailMaxLevels = 8;
-constexpr size_t kTailSmemBudget = 200 * 1024;
-struct TailArgs {
-    int n = 0;
-    Level lv[kTailMaxLevels + 1];
-    int soff[kTailMaxLevels + 1] = {};
-    const float* g = nullptr;                        // G_t planes
-    float* hi[kTailMaxLevels] = {};
-    float* lo[kTailMaxLevels] = {};
-    float gain[kTailMaxLevels] = {};
-    float* cur_out = nullptr;                        // cur_t planes (null: analysis only)
-    float* g_last = nullptr;                         // G_{t+n} planes (null: not kept)
-    int first = 0;
-    double c_hi = 0, omc_hi = 0, c_lo = 0, omc_lo = 0;
-};
-size_t tail_smem_bytes(const Level* lv, int n);
-cudaError_t launch_tail(TailArgs& a, int planes, cudaStream_t s);
 
 // PreprocessProcessor + GrayscaleProcessor on the device (mc_preprocess.cu)
 cudaError_t launch_preprocess(const uint8_t* src_roi, size_t step, int cn, int sw, int sh, int dw, int dh, bool copy_only,

@@ -71,11 +71,8 @@ __device__ __forceinline__ float down5(float a, float b, float c, float d, float
 // lab16: pointwise, 4 pixels per thread (12 input bytes = three 32-bit words).
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_lab16(const uint8_t* __restrict__ in, size_t in_step, size_t in_lane_stride,
-                                               int w, int h, const LabLutEntry* __restrict__ lut,
+                                               int w, int h, const LabLutCell* __restrict__ lut,
                                                int16_t* __restrict__ lab, int pitch16, size_t plane16, int aligned) {
-    __shared__ uint16_t s_tx[256];   // u8 sample -> (LUT cell << 8 | 4-bit weight), see lab_tx_of_u8
-    s_tx[threadIdx.x] = (uint16_t)lab_tx_of_u8(threadIdx.x);
-    __syncthreads();
     const int lane = blockIdx.z;
     const int y = blockIdx.y;
     const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
@@ -99,7 +96,7 @@ __global__ void __launch_bounds__(256) k_lab16(const uint8_t* __restrict__ in, s
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         int sL, sA, sB;
-        lab_fixed_from_tx(s_tx[px[3 * i]], s_tx[px[3 * i + 1]], s_tx[px[3 * i + 2]], lut, sL, sA, sB);
+        lab_fixed_from_q(lab_q_of_u8(px[3 * i]), lab_q_of_u8(px[3 * i + 1]), lab_q_of_u8(px[3 * i + 2]), lut, sL, sA, sB);
         L[i] = (short)sL; A[i] = (short)sA; B[i] = (short)sB;
     }
     int16_t* o = lab + (size_t)(lane * 3) * plane16 + (size_t)y * pitch16 + x;  // pitch16 % 64 == 0, x % 4 == 0
@@ -463,79 +460,56 @@ __global__ void __launch_bounds__(32 * DS_WARPS) k_down_strip(const DownArgs a) 
 // ------------------------------------------------------------------------------------------------
 // ingest_lab: u8 BGR -> Lab (exact OpenCV LUT) -> { Lab16 planes for egress, G1 = pyrDown(Lab) } in one
 // pass.  Same strip structure as down_strip (row pass by shuffles, column pass as a register window),
-// with the three Lab channels carried together; the LUT gathers (L1-bound) hide the stencil math.
+// with the three Lab channels carried together.  The kernel is bound by the divergent LUT gathers (L1 tag
+// lookups) and by issue slots, not by HBM: each pixel costs two 256-bit gathers (LabLutCell) and ~80 instructions;
+// the next row's 12 input bytes per lane are requested before the current row is converted.
 // ------------------------------------------------------------------------------------------------
 constexpr int IG_ROWS = 32;   // coarse rows per warp (halo rows re-convert 4 of 68 fine rows)
-constexpr int IG_WARPS = 1;   // one warp per CTA: 5k+ independent CTAs per 16-lane step, no wave-quantisation tail
 
 struct IngestArgs {
     const uint8_t* in; size_t in_step, in_lane_stride;
     int w, h, aligned;
-    const LabLutEntry* lut;
+    const LabLutCell* lut;
     int16_t* lab; int pitch16; size_t plane16;
     float* g1; Level l1;
 };
 
-struct Lab4 { float L[4], A[4], B[4]; };
+struct IgRaw { uint32_t w0, w1, w2; };   // 4 BGR pixels of one lane
 
-// COMPACT (option ingest_compact): the LUT gathers are the kernel's bottleneck (L1 wavefronts: every distinct 128-byte
-// line a warp-wide load touches costs one).  With the natural mapping the 32 lanes of one gather instruction hold pixels
-// 4 columns apart across a 128-pixel span; in COMPACT mode the row's pixels take a detour through shared memory so that
-// each gather instruction serves 32 ADJACENT pixels (which share LUT cells far more often), and the lanes pick up
-// their own four columns afterwards.  Same values, bit for bit.
-template <bool COMPACT>
-__device__ __forceinline__ void ig_row(const IngestArgs& a, const uint16_t* s_tx, const uint8_t* frame, int row, int gx,
-                                       bool fast, bool own, int16_t* lab_lane, float (&hL)[2], float (&hA)[2],
-                                       float (&hB)[2], uint32_t* s_raw, short (*s_lab)[128]) {
-    // loads 4 BGR pixels of fine row `row` (reflected), converts, optionally stores Lab16, returns the row pass
-    const int ry = reflect101(row, a.h);
-    const uint8_t* p = frame + (size_t)ry * a.in_step;
-    uint32_t px[12];
+__device__ __forceinline__ IgRaw ig_load(const IngestArgs& a, const uint8_t* frame, int row, int gx, bool fast) {
+    const uint8_t* p = frame + (size_t)reflect101(row, a.h) * a.in_step;
+    IgRaw r;
     if (fast) {
         const uint32_t* q = reinterpret_cast<const uint32_t*>(p + (size_t)gx * 3);
-        const uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            px[i] = (w0 >> (8 * i)) & 0xff;
-            px[4 + i] = (w1 >> (8 * i)) & 0xff;
-            px[8 + i] = (w2 >> (8 * i)) & 0xff;
-        }
+        r.w0 = __ldg(q); r.w1 = __ldg(q + 1); r.w2 = __ldg(q + 2);
     } else {
+        uint32_t px[12];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const uint8_t* q = p + (size_t)reflect101(gx + i, a.w) * 3;
             px[3 * i] = __ldg(q); px[3 * i + 1] = __ldg(q + 1); px[3 * i + 2] = __ldg(q + 2);
         }
+        r.w0 = px[0] | (px[1] << 8) | (px[2] << 16) | (px[3] << 24);
+        r.w1 = px[4] | (px[5] << 8) | (px[6] << 16) | (px[7] << 24);
+        r.w2 = px[8] | (px[9] << 8) | (px[10] << 16) | (px[11] << 24);
+    }
+    return r;
+}
+
+// converts the lane's 4 pixels of fine row `row`, optionally stores Lab16, returns the row pass of the three channels
+__device__ __forceinline__ void ig_row(const IngestArgs& a, const IgRaw raw, int row, int gx, bool own, int16_t* lab_lane,
+                                       float (&hL)[2], float (&hA)[2], float (&hB)[2]) {
+    uint32_t px[12];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        px[i] = (raw.w0 >> (8 * i)) & 0xff;
+        px[4 + i] = (raw.w1 >> (8 * i)) & 0xff;
+        px[8 + i] = (raw.w2 >> (8 * i)) & 0xff;
     }
     int sL[4], sA[4], sB[4];
-    if (COMPACT) {
-        const int lane = threadIdx.x & 31;
-        // the lane's 12 bytes -> strip order in shared memory (3 words per lane)
-        s_raw[3 * lane] = px[0] | (px[1] << 8) | (px[2] << 16) | (px[3] << 24);
-        s_raw[3 * lane + 1] = px[4] | (px[5] << 8) | (px[6] << 16) | (px[7] << 24);
-        s_raw[3 * lane + 2] = px[8] | (px[9] << 8) | (px[10] << 16) | (px[11] << 24);
-        __syncwarp();
-        const uint8_t* rb = reinterpret_cast<const uint8_t*>(s_raw);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int p = lane + 32 * i;            // 32 adjacent pixels per gather instruction
-            int cl, ca, cb;
-            lab_fixed_from_tx(s_tx[rb[3 * p]], s_tx[rb[3 * p + 1]], s_tx[rb[3 * p + 2]], a.lut, cl, ca, cb);
-            s_lab[0][p] = (short)cl; s_lab[1][p] = (short)ca; s_lab[2][p] = (short)cb;
-        }
-        __syncwarp();
-        const short4 qL = *reinterpret_cast<const short4*>(&s_lab[0][4 * lane]);
-        const short4 qA = *reinterpret_cast<const short4*>(&s_lab[1][4 * lane]);
-        const short4 qB = *reinterpret_cast<const short4*>(&s_lab[2][4 * lane]);
-        sL[0] = qL.x; sL[1] = qL.y; sL[2] = qL.z; sL[3] = qL.w;
-        sA[0] = qA.x; sA[1] = qA.y; sA[2] = qA.z; sA[3] = qA.w;
-        sB[0] = qB.x; sB[1] = qB.y; sB[2] = qB.z; sB[3] = qB.w;
-        __syncwarp();                               // the buffers are reused by the next row
-    } else {
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-            lab_fixed_from_tx(s_tx[px[3 * i]], s_tx[px[3 * i + 1]], s_tx[px[3 * i + 2]], a.lut, sL[i], sA[i], sB[i]);
-    }
+    for (int i = 0; i < 4; ++i)
+        lab_fixed_from_q(lab_q_of_u8((int)px[3 * i]), lab_q_of_u8((int)px[3 * i + 1]), lab_q_of_u8((int)px[3 * i + 2]), a.lut, sL[i], sA[i], sB[i]);
     if (own) {   // this warp owns the row and the lane owns the columns: emit the Lab16 planes
         int16_t* o = lab_lane + (size_t)row * a.pitch16 + gx;
         *reinterpret_cast<short4*>(o) = make_short4((short)sL[0], (short)sL[1], (short)sL[2], (short)sL[3]);
@@ -555,19 +529,12 @@ __device__ __forceinline__ void ig_row(const IngestArgs& a, const uint16_t* s_tx
     o = ds_rowpass(r); hB[0] = o.h0; hB[1] = o.h1;
 }
 
-template <bool COMPACT>
-__global__ void __launch_bounds__(32 * IG_WARPS) k_ingest_lab(const IngestArgs a) {
-    __shared__ uint16_t s_tx[256];
-    __shared__ __align__(16) uint32_t s_raw_all[COMPACT ? IG_WARPS : 1][COMPACT ? 96 : 1];
-    __shared__ __align__(16) short s_lab_all[COMPACT ? IG_WARPS : 1][COMPACT ? 3 : 1][128];
-    for (int i = threadIdx.x; i < 256; i += 32 * IG_WARPS) s_tx[i] = (uint16_t)lab_tx_of_u8(i);
-    __syncthreads();
+template <int WARPS>
+__global__ void __launch_bounds__(32 * WARPS) k_ingest_lab(const IngestArgs a) {
     const int lane_id = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t* s_raw = s_raw_all[COMPACT ? warp : 0];
-    short (*s_lab)[128] = s_lab_all[COMPACT ? warp : 0];
     const int lane = blockIdx.z;                                       // stream
     const int gx = blockIdx.x * DS_COLS - 4 + lane_id * 4;
-    const int k0 = (blockIdx.y * IG_WARPS + warp) * IG_ROWS;
+    const int k0 = (blockIdx.y * WARPS + warp) * IG_ROWS;
     const int wc = a.l1.w, hc = a.l1.h;
     if (k0 >= hc) return;
     const int k_end = min(k0 + IG_ROWS, hc);
@@ -581,16 +548,21 @@ __global__ void __launch_bounds__(32 * IG_WARPS) k_ingest_lab(const IngestArgs a
 
     // window[c][i] = row pass of fine row (2k-2+i), channel c, for the lane's two coarse columns
     float wL[4][2], wA[4][2], wB[4][2];
+    IgRaw nxt = ig_load(a, frame, 2 * k0 - 2, gx, fast);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int row = 2 * k0 - 2 + i;
-        ig_row<COMPACT>(a, s_tx, frame, row, gx, fast, col_owner && row >= 2 * k0 && row < a.h, lab_lane, wL[i], wA[i], wB[i], s_raw, s_lab);
+        const IgRaw cur = nxt;
+        nxt = ig_load(a, frame, row + 1, gx, fast);
+        ig_row(a, cur, row, gx, col_owner && row >= 2 * k0 && row < a.h, lab_lane, wL[i], wA[i], wB[i]);
     }
     for (int k = k0; k < k_end; ++k) {
         float nL[2], nA[2], nB[2];
         {
             const int row = 2 * k + 2;
-            ig_row<COMPACT>(a, s_tx, frame, row, gx, fast, col_owner && row < 2 * k_end && row < a.h, lab_lane, nL, nA, nB, s_raw, s_lab);
+            const IgRaw cur = nxt;
+            nxt = ig_load(a, frame, row + 1, gx, fast);
+            ig_row(a, cur, row, gx, col_owner && row < 2 * k_end && row < a.h, lab_lane, nL, nA, nB);
         }
         if (writer) {
             float* q = oL + (size_t)k * a.l1.pitch + jx;
@@ -611,8 +583,11 @@ __global__ void __launch_bounds__(32 * IG_WARPS) k_ingest_lab(const IngestArgs a
         {
             const int row = 2 * k + 3;
             const bool need = k + 1 < k_end;   // the last iteration's extra row is never used
-            if (need) ig_row<COMPACT>(a, s_tx, frame, row, gx, fast, col_owner && row < 2 * k_end && row < a.h, lab_lane, mL, mA, mB, s_raw, s_lab);
-            else { mL[0] = mL[1] = mA[0] = mA[1] = mB[0] = mB[1] = 0.f; }
+            if (need) {
+                const IgRaw cur = nxt;
+                nxt = ig_load(a, frame, row + 1, gx, fast);
+                ig_row(a, cur, row, gx, col_owner && row < 2 * k_end && row < a.h, lab_lane, mL, mA, mB);
+            } else { mL[0] = mL[1] = mA[0] = mA[1] = mB[0] = mB[1] = 0.f; }
         }
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
@@ -867,109 +842,6 @@ __global__ void __launch_bounds__(256) k_egress(const EgressArgs a) {
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// tail: the coarse end of the pyramid in ONE launch (option use_tail).  Levels >= 3 of a 1080p frame hold a few
-// thousand pixels each; as separate launches they cost ~10 us apiece for microseconds of work.  Here one CTA owns
-// one plane (lane x channel) and keeps its levels t .. L resident in shared memory (at most ~200 KB, unpadded
-// rows): for each level pyrDown, band = G - pyrUp(G_next), both EMA updates (the only HBM traffic besides the
-// input plane), gain; then the collapse up to cur_t, which is the only plane written back.  Same arithmetic and
-// operation order as k_level / k_collapse (cv::pyrDown / pyrUp border rules applied to indices).
-// ------------------------------------------------------------------------------------------------
-#if defined(MC_CUDA_EMU)
-#define MC_DYN_SMEM(name) float* name = static_cast<float*>(cuda_emu::dyn_smem())
-#else
-#define MC_DYN_SMEM(name) extern __shared__ __align__(16) float name[]
-#endif
-
-__device__ __forceinline__ float tail_pyrup_at(const float* __restrict__ c, int wc, int hc, int y, int x) {
-    const int i = x >> 1, j = y >> 1;
-    const int im = upsrc(i - 1, wc), ip = upsrc(i + 1, wc);
-    const bool xodd = x & 1, yodd = y & 1;
-    float r[3];
-#pragma unroll
-    for (int q = 0; q < 3; ++q) {
-        const float* row = c + upsrc(j - 1 + q, hc) * wc;
-        r[q] = xodd ? (row[i] + row[ip]) * 4.0f : (row[im] + row[i] * 6.0f + row[ip]);
-    }
-    return yodd ? ((r[1] + r[2]) * 4.0f) * kInv64 : (r[0] + r[1] * 6.0f + r[2]) * kInv64;
-}
-
-__global__ void __launch_bounds__(1024) k_tail(const TailArgs a) {
-    MC_DYN_SMEM(S);
-    const int plane = blockIdx.x;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-    {
-        const Level L0 = a.lv[0];
-        const float* __restrict__ src = a.g + (size_t)plane * L0.plane;
-        float* dst = S + a.soff[0];
-        for (int y = warp; y < L0.h; y += nw)
-            for (int x = lane; x < L0.w; x += 32) dst[y * L0.w + x] = __ldg(src + (size_t)y * L0.pitch + x);
-    }
-    __syncthreads();
-    for (int l = 0; l < a.n; ++l) {
-        const Level F = a.lv[l], C = a.lv[l + 1];
-        float* f = S + a.soff[l];
-        float* c = S + a.soff[l + 1];
-        // pyrDown: row pass of the five source rows, then the column pass (same order as k_level)
-        for (int y = warp; y < C.h; y += nw)
-            for (int x = lane; x < C.w; x += 32) {
-                const int x0 = reflect101(2 * x - 2, F.w), x1 = reflect101(2 * x - 1, F.w), x2 = 2 * x,
-                          x3 = reflect101(2 * x + 1, F.w), x4 = reflect101(2 * x + 2, F.w);
-                float hr[5];
-#pragma unroll
-                for (int q = 0; q < 5; ++q) {
-                    const float* p = f + reflect101(2 * y - 2 + q, F.h) * F.w;
-                    hr[q] = down5(p[x0], p[x1], p[x2], p[x3], p[x4]);
-                }
-                c[y * C.w + x] = down5(hr[0], hr[1], hr[2], hr[3], hr[4]) * kInv256;
-            }
-        __syncthreads();
-        // band + temporal filter; the amplified band replaces G_l in shared memory
-        float* __restrict__ hi = a.hi[l] + (size_t)plane * F.plane;
-        float* __restrict__ lo = a.lo[l] + (size_t)plane * F.plane;
-        const float gain = a.gain[l];
-        for (int y = warp; y < F.h; y += nw)
-            for (int x = lane; x < F.w; x += 32) {
-                const float band = f[y * F.w + x] - tail_pyrup_at(c, C.w, C.h, y, x);
-                const size_t o = (size_t)y * F.pitch + x;
-                if (a.first) {
-                    hi[o] = band;
-                    lo[o] = band;
-                } else {
-                    const float nh = ema(hi[o], band, a.omc_hi, a.c_hi), nl = ema(lo[o], band, a.omc_lo, a.c_lo);
-                    hi[o] = nh;
-                    lo[o] = nl;
-                    f[y * F.w + x] = (nh - nl) * gain;
-                }
-            }
-        __syncthreads();
-    }
-    if (a.g_last) {   // G_{t+n}: the residual level (kept for the faithful option's state copy)
-        const Level R = a.lv[a.n];
-        const float* src = S + a.soff[a.n];
-        float* dst = a.g_last + (size_t)plane * R.plane;
-        for (int y = warp; y < R.h; y += nw)
-            for (int x = lane; x < R.w; x += 32) dst[(size_t)y * R.pitch + x] = src[y * R.w + x];
-    }
-    if (a.first || !a.cur_out) return;
-    // collapse: cur_{top} = m_{top} (the residual above it is zeroed, MagnifyCore.hpp:130-131), cur_l = pyrUp(cur_{l+1}) + m_l
-    for (int l = a.n - 2; l >= 0; --l) {
-        const Level F = a.lv[l], C = a.lv[l + 1];
-        float* f = S + a.soff[l];
-        const float* c = S + a.soff[l + 1];
-        for (int y = warp; y < F.h; y += nw)
-            for (int x = lane; x < F.w; x += 32) f[y * F.w + x] = tail_pyrup_at(c, C.w, C.h, y, x) + f[y * F.w + x];
-        __syncthreads();
-    }
-    {
-        const Level L0 = a.lv[0];
-        const float* src = S + a.soff[0];
-        float* dst = a.cur_out + (size_t)plane * L0.plane;
-        for (int y = warp; y < L0.h; y += nw)
-            for (int x = lane; x < L0.w; x += 32) dst[(size_t)y * L0.pitch + x] = src[y * L0.w + x];
-    }
-}
-
 __global__ void k_copy(float* __restrict__ dst, const float* __restrict__ src, size_t n) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
         dst[i] = src[i];
@@ -1021,15 +893,17 @@ cudaError_t launch_lab16(const FrameIO& io, const DeviceTables& tb, int16_t* lab
 }
 
 cudaError_t launch_ingest_lab(const FrameIO& io, const DeviceTables& tb, int16_t* lab, int pitch16, size_t plane16,
-                              float* g1, const Level& l1, cudaStream_t s, bool compact) {
+                              float* g1, const Level& l1, cudaStream_t s, int warps) {
     IngestArgs a;
     a.in = io.in; a.in_step = io.in_step; a.in_lane_stride = io.in_lane_stride;
     a.w = io.w; a.h = io.h;
     a.aligned = (reinterpret_cast<uintptr_t>(io.in) % 4 == 0) && (io.in_step % 4 == 0) && (io.in_lane_stride % 4 == 0);
     a.lut = tb.lab_lut; a.lab = lab; a.pitch16 = pitch16; a.plane16 = plane16; a.g1 = g1; a.l1 = l1;
-    dim3 grid(cdiv(io.w, DS_COLS), cdiv(l1.h, IG_ROWS * IG_WARPS), io.lanes);
-    if (compact) k_ingest_lab<true><<<grid, 32 * IG_WARPS, 0, s>>>(a);
-    else k_ingest_lab<false><<<grid, 32 * IG_WARPS, 0, s>>>(a);
+    if (warps != 2 && warps != 4) warps = 1;
+    dim3 grid(cdiv(io.w, DS_COLS), cdiv(l1.h, IG_ROWS * warps), io.lanes);
+    if (warps == 4) k_ingest_lab<4><<<grid, 128, 0, s>>>(a);
+    else if (warps == 2) k_ingest_lab<2><<<grid, 64, 0, s>>>(a);
+    else k_ingest_lab<1><<<grid, 32, 0, s>>>(a);
     return cudaGetLastError();
 }
 
@@ -1088,28 +962,6 @@ cudaError_t launch_egress(const FrameIO& io, const DeviceTables& tb, const int16
     dim3 grid(cdiv(io.w, TW), cdiv(io.h, TH), io.lanes);
     if (io.channels == 3) k_egress<3><<<grid, 256, 0, s>>>(a);
     else k_egress<1><<<grid, 256, 0, s>>>(a);
-    return cudaGetLastError();
-}
-
-size_t tail_smem_bytes(const Level* lv, int n) {
-    size_t floats = 0;
-    for (int l = 0; l <= n; ++l) floats += ((size_t)lv[l].w * lv[l].h + 3) / 4 * 4;
-    return floats * sizeof(float);
-}
-
-cudaError_t launch_tail(TailArgs& a, int planes, cudaStream_t s) {
-    int off = 0;
-    for (int l = 0; l <= a.n; ++l) {
-        a.soff[l] = off;
-        off += (a.lv[l].w * a.lv[l].h + 3) / 4 * 4;
-    }
-    const size_t bytes = (size_t)off * sizeof(float);
-    // opt in to > 48 KB of dynamic shared memory: a per-device function attribute, cheap to set, so it is set on every
-    // launch (always to the full budget: handles on several devices / threads agree on the value)
-    if (bytes > kTailSmemBudget) return cudaErrorInvalidValue;
-    const cudaError_t e = cudaFuncSetAttribute(k_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTailSmemBudget);
-    if (e != cudaSuccess) return e;
-    k_tail<<<planes, 1024, bytes, s>>>(a);
     return cudaGetLastError();
 }
 

@@ -16,9 +16,15 @@ namespace mc {
 constexpr int kLabLutDim = 33;          // OpenCV LAB_LUT_DIM
 constexpr int kGammaTabSize = 1024;     // OpenCV GAMMA_TAB_SIZE
 
-// One packed LUT entry: Lab int16 values of lattice points (b,g,r) [index 0] and (b,g,r+1) [index 1],
-// interleaved per channel so that one dp2a does the r-interpolation of a channel.
-struct alignas(16) LabLutEntry { int16_t v[8]; };  // {L0,L1,a0,a1,b0,b1,0,0}
+// One packed LUT cell (32 B = one L1/L2 sector): the Lab int16 values of the lattice points (b, g..g+1, r..r+1),
+// interleaved so that one dp2a does the r-interpolation of a channel at one (b, g) corner.  A pixel needs two cells,
+// (b, g, r) and (b+1, g, r), each fetched with ONE 256-bit load (LDG.E.256 on sm_100) — the divergent LUT gathers are
+// what bounds the BGR->Lab kernels (L1 tag lookups per distinct sector), so bytes per gather instruction is the lever.
+// The table is [34][33][33]: g+1 / r+1 are clamped when the table is built and the b = 33 slab repeats b = 32, so the
+// device code needs no clamping (a clamped neighbour always has weight 0).
+struct alignas(32) LabLutCell { int16_t v[16]; };  // {L00,L01, a00,a01, b00,b01, L10,L11, a10,a11, b10,b11, 0,0,0,0}, index = (g-offset, r-offset)
+constexpr int kLabLutSlab = kLabLutDim * kLabLutDim;   // cells per b slab
+constexpr int kLabLutCells = (kLabLutDim + 1) * kLabLutSlab;
 
 MC_HD int reflect101(int i, int n) {
     if (i < 0) i = -i;
@@ -71,57 +77,74 @@ MC_HD uint8_t scaled_to_u8(float x, float a, float b) {
 #define MC_LDG16(p) __ldg(reinterpret_cast<const int4*>(p))
 #endif
 
-// Per-channel quantisation of a u8 sample as OpenCV's float path sees it: cx = round(v*(1/255)*2^14),
-// LUT cell t = cx >> 9 and 4-bit weight x = (cx >> 5) & 15.  Returned packed as (t << 8) | x.
-MC_HD int lab_tx_of_u8(int v) {
+// Per-channel quantisation of a u8 sample as OpenCV's float path sees it: cx = cvRound(v*(1/255)*2^14),
+// LUT cell t = cx >> 9 and 4-bit weight x = (cx >> 5) & 15.  Returned packed as q = cx >> 5 = (t << 4) | x.
+// cx equals (v*16448 + 128) >> 8 for all 256 inputs (tests/test_host.py checks it against the float form), so the
+// kernels compute q with one IMAD and a shift instead of a table lookup.
+MC_HD int lab_q_of_u8_float(int v) {   // the definition (float arithmetic of convertTo + cvtColor)
     const float c = ((float)v * 0.003921568859368563f) * 16384.0f;
 #if defined(__CUDA_ARCH__)
     const int cx = __float2int_rn(c);
 #else
     const int cx = (int)lrintf(c);
 #endif
-    return ((cx >> 9) << 8) | ((cx >> 5) & 15);
+    return cx >> 5;
 }
+MC_HD int lab_q_of_u8(int v) { return (v * 16448 + 128) >> 13; }
+
+#if defined(__CUDA_ARCH__)
+// one LUT cell = one 256-bit read-only load
+__device__ __forceinline__ void ldg_cell(const LabLutCell* p, int (&w)[8]) {
+#if defined(MC_CUDA_EMU)
+    const int* q = reinterpret_cast<const int*>(p);
+    for (int i = 0; i < 8; ++i) w[i] = q[i];
+#else
+    asm("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "l"(p));
+#endif
+}
+#endif
 
 // cv::cvtColor(COLOR_BGR2Lab) on CV_32F input that came from u8/255 — bit-exact restatement of
 // OpenCV's 33^3 int16 LUT + 4-bit fixed-point trilinear interpolation.
-// lut is [b][g][r] packed entries; txb/txg/txr are lab_tx_of_u8() of the three samples (the kernels read
-// them from a 256-entry shared-memory table).  Fixed-point result: L*2^14/100, (a+128)*64, (b+128)*64.
-MC_HD void lab_fixed_from_tx(int txb, int txg, int txr, const LabLutEntry* __restrict__ lut, int& sL, int& sA, int& sB) {
-    const int tb = txb >> 8, tg = txg >> 8, tr = txr >> 8;
-    const int xb = txb & 15, xg = txg & 15, xr = txr & 15;
-    const int tb1 = tb + 1 > 32 ? 32 : tb + 1, tg1 = tg + 1 > 32 ? 32 : tg + 1;
-    const LabLutEntry* e00 = lut + ((tb * kLabLutDim + tg) * kLabLutDim + tr);
-    const int dg = (tg1 - tg) * kLabLutDim, db = (tb1 - tb) * kLabLutDim * kLabLutDim;
-    const int w00 = (16 - xb) * (16 - xg), w01 = (16 - xb) * xg, w10 = xb * (16 - xg), w11 = xb * xg;
+// qb/qg/qr are lab_q_of_u8() of the three samples.  Fixed-point result: L*2^14/100, (a+128)*64, (b+128)*64.
+MC_HD void lab_fixed_from_q(int qb, int qg, int qr, const LabLutCell* __restrict__ lut, int& sL, int& sA, int& sB) {
+    const int tb = qb >> 4, tg = qg >> 4, tr = qr >> 4;
+    const int xb = qb & 15, xg = qg & 15, xr = qr & 15;
+    const LabLutCell* c0 = lut + ((tb * kLabLutDim + tg) * kLabLutDim + tr);
+    const int w01 = (16 - xb) * xg, w00 = ((16 - xb) << 4) - w01, w11 = xb * xg, w10 = (xb << 4) - w11;
 #if defined(__CUDA_ARCH__)
-    const int wr = (16 - xr) | (xr << 8);                       // int8 pair for dp2a: lo * (16-x) + hi * x
-    const int4 q00 = MC_LDG16(e00), q01 = MC_LDG16(e00 + dg), q10 = MC_LDG16(e00 + db), q11 = MC_LDG16(e00 + db + dg);
-    sL = w00 * __dp2a_lo(q00.x, wr, 0) + w01 * __dp2a_lo(q01.x, wr, 0) + w10 * __dp2a_lo(q10.x, wr, 0) + w11 * __dp2a_lo(q11.x, wr, 0);
-    sA = w00 * __dp2a_lo(q00.y, wr, 0) + w01 * __dp2a_lo(q01.y, wr, 0) + w10 * __dp2a_lo(q10.y, wr, 0) + w11 * __dp2a_lo(q11.y, wr, 0);
-    sB = w00 * __dp2a_lo(q00.z, wr, 0) + w01 * __dp2a_lo(q01.z, wr, 0) + w10 * __dp2a_lo(q10.z, wr, 0) + w11 * __dp2a_lo(q11.z, wr, 0);
+    int u[8], v[8];
+    ldg_cell(c0, u);
+    ldg_cell(c0 + kLabLutSlab, v);
+    const int wr = 16 + 255 * xr;                               // int8 pair for dp2a: lo * (16-x) + hi * x
+    sL = w00 * __dp2a_lo(u[0], wr, 0) + (w01 * __dp2a_lo(u[3], wr, 0) + (w10 * __dp2a_lo(v[0], wr, 0) + (w11 * __dp2a_lo(v[3], wr, 0) + 2048)));
+    sA = w00 * __dp2a_lo(u[1], wr, 0) + (w01 * __dp2a_lo(u[4], wr, 0) + (w10 * __dp2a_lo(v[1], wr, 0) + (w11 * __dp2a_lo(v[4], wr, 0) + 2048)));
+    sB = w00 * __dp2a_lo(u[2], wr, 0) + (w01 * __dp2a_lo(u[5], wr, 0) + (w10 * __dp2a_lo(v[2], wr, 0) + (w11 * __dp2a_lo(v[5], wr, 0) + 2048)));
 #else
-    const LabLutEntry* es[4] = {e00, e00 + dg, e00 + db, e00 + db + dg};
-    const int ws[4] = {w00, w01, w10, w11};
-    sL = sA = sB = 0;
-    for (int i = 0; i < 4; ++i) {
-        sL += ws[i] * ((16 - xr) * es[i]->v[0] + xr * es[i]->v[1]);
-        sA += ws[i] * ((16 - xr) * es[i]->v[2] + xr * es[i]->v[3]);
-        sB += ws[i] * ((16 - xr) * es[i]->v[4] + xr * es[i]->v[5]);
-    }
+    const LabLutCell* cs[2] = {c0, c0 + kLabLutSlab};
+    const int ws[2][2] = {{w00, w01}, {w10, w11}};
+    sL = sA = sB = 2048;
+    for (int ib = 0; ib < 2; ++ib)
+        for (int ig = 0; ig < 2; ++ig) {
+            const int16_t* e = cs[ib]->v + 6 * ig;
+            sL += ws[ib][ig] * ((16 - xr) * e[0] + xr * e[1]);
+            sA += ws[ib][ig] * ((16 - xr) * e[2] + xr * e[3]);
+            sB += ws[ib][ig] * ((16 - xr) * e[4] + xr * e[5]);
+        }
 #endif
-    sL = (sL + 2048) >> 12;
-    sA = (sA + 2048) >> 12;
-    sB = (sB + 2048) >> 12;
+    sL >>= 12;
+    sA >>= 12;
+    sB >>= 12;
 }
 
-MC_HD void bgr_u8_to_lab_fixed(uint8_t b8, uint8_t g8, uint8_t r8, const LabLutEntry* __restrict__ lut,
+MC_HD void bgr_u8_to_lab_fixed(uint8_t b8, uint8_t g8, uint8_t r8, const LabLutCell* __restrict__ lut,
                                int& sL, int& sA, int& sB) {
-    lab_fixed_from_tx(lab_tx_of_u8(b8), lab_tx_of_u8(g8), lab_tx_of_u8(r8), lut, sL, sA, sB);
+    lab_fixed_from_q(lab_q_of_u8(b8), lab_q_of_u8(g8), lab_q_of_u8(r8), lut, sL, sA, sB);
 }
 
 // Float Lab as OpenCV returns it: L in [0,100], a,b in [-128,128).
-MC_HD void bgr_u8_to_lab(uint8_t b8, uint8_t g8, uint8_t r8, const LabLutEntry* __restrict__ lut,
+MC_HD void bgr_u8_to_lab(uint8_t b8, uint8_t g8, uint8_t r8, const LabLutCell* __restrict__ lut,
                          float& L, float& A, float& B) {
     int sL, sA, sB;
     bgr_u8_to_lab_fixed(b8, g8, r8, lut, sL, sA, sB);

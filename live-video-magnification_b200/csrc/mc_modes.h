@@ -36,14 +36,11 @@ struct ModeCtx {
     float* float_out;  // optional [lanes][h][w][C] pre-quantisation tap
     Profiler* prof;    // optional
     bool use_tma;      // stage level-kernel tiles with cp.async.bulk.tensor (option "use_tma", default on)
-    bool prefetch_state;    // level kernel requests its state tiles by TMA at kernel entry (option "prefetch_state", default off
-                            // until measured on the B200)
-    bool use_tail;          // levels >= MotionMode::tail_start run in the single fused tail kernel (option "use_tail", default off
-                            // until measured on the B200)
-    bool ingest_compact;    // ingest: each LUT gather instruction serves 32 adjacent pixels (option "ingest_compact", default off
-                            // until measured on the B200)
+    bool prefetch_state;    // level kernel requests its state tiles by TMA at kernel entry (option "prefetch_state", default on:
+                            // B200, 32 lanes: level[1] 235 -> 205 us)
+    int ingest_warps;       // warps per CTA of the fused ingest kernel (option "ingest_warps": 1, 2 or 4)
     bool band_from_state;   // synthesis rebuilds gain*(hi-lo) from the state planes instead of reading a stored band
-                            // (option "band_from_state", default off: measured no faster on B200)
+                            // (option "band_from_state", default on: with prefetch_state level[1] 205 -> 177 us, egress +8 us)
     bool analysis_only;     // Laplace / Phase: update the temporal state but skip synthesis + egress (*produced = 0); used by the
                             // state-carry pass of temporal sharding (lvm_b200.shard.magnify_segment)
 };
@@ -99,7 +96,6 @@ struct MotionMode {
     DeviceArena arena;
 
     std::vector<TensorMapStorage> tmaps;   // per level: TMA descriptor of G[l] (tmap_valid[l] != 0)
-    int tail_start = 0;                    // first level of the fused tail kernel (0: none fits), option use_tail
     std::vector<TensorMapStorage> tmaps_hi, tmaps_lo;   // ... and of the state planes (64 x 32 tiles, option prefetch_state)
     std::vector<char> tmap_valid;
     std::vector<float> gains;              // per-level gains of the current frame (member: no per-frame allocation)

@@ -88,10 +88,6 @@ mc_status MotionMode::allocate(const ModeCtx& ctx, const FrameIO& io, int nlevel
         MCK(arena.alloc_bytes(&p, planes * plane16 * sizeof(int16_t)));
         lab16 = (int16_t*)p;
     }
-    // fused tail (option use_tail): the first level >= 2 from which all coarser planes fit one CTA's shared memory
-    tail_start = 0;
-    for (int l = 2; l <= levels - 2 && !tail_start; ++l)
-        if (levels - l <= kTailMaxLevels && tail_smem_bytes(&lv[(size_t)l], levels - l) <= kTailSmemBudget) tail_start = l;
     allocated = true;
     return MC_OK;
 }
@@ -111,13 +107,12 @@ mc_status MotionMode::process(const ModeCtx& ctx, const FrameIO& io, const mc_pa
     // ingest: u8 BGR -> Lab16 planes (gray frames are read directly by the level-0 kernel)
     // (production path, >= 2 levels: one fused kernel also builds G1; otherwise Lab16 alone)
     const bool fused_ingest = channels == 3 && !faithful && levels >= 2;
-    if (fused_ingest) LAUNCH("ingest_lab", 0, launch_ingest_lab(io, *ctx.tables, lab16, pitch16, plane16, G[1], lv[1], ctx.stream, ctx.ingest_compact));
+    if (fused_ingest) LAUNCH("ingest_lab", 0, launch_ingest_lab(io, *ctx.tables, lab16, pitch16, plane16, G[1], lv[1], ctx.stream, ctx.ingest_warps));
     else if (channels == 3) LAUNCH("lab16", 0, launch_lab16(io, *ctx.tables, lab16, pitch16, plane16, ctx.stream));
 
     // analysis: one fused kernel per level (level 0 only builds G1 unless the faithful option is on)
     const int l_begin = fused_ingest ? 1 : ((levels >= 2 || faithful) ? 0 : levels);
-    const int l_tail = (ctx.use_tail && tail_start) ? tail_start : levels;   // levels >= l_tail run in the fused tail kernel
-    for (int l = l_begin; l < l_tail; ++l) {
+    for (int l = l_begin; l < levels; ++l) {
         LevelArgs a;
         if (l == 0) {
             if (channels == 3) {
@@ -148,22 +143,6 @@ mc_status MotionMode::process(const ModeCtx& ctx, const FrameIO& io, const mc_pa
         if (a.band) LAUNCH("level", l, launch_level(a, ctx.stream));
         else LAUNCH("down", l, launch_down(a, ctx.stream));
     }
-    if (l_tail < levels) {
-        TailArgs t;
-        t.n = levels - l_tail;
-        for (int l = l_tail; l <= levels; ++l) t.lv[l - l_tail] = lv[(size_t)l];
-        for (int l = l_tail; l < levels; ++l) {
-            t.hi[l - l_tail] = hi[(size_t)l];
-            t.lo[l - l_tail] = lo[(size_t)l];
-            t.gain[l - l_tail] = gains[(size_t)l];
-        }
-        t.g = G[(size_t)l_tail];
-        t.g_last = G[(size_t)levels];
-        t.cur_out = (first || ctx.analysis_only) ? nullptr : M[(size_t)l_tail];
-        t.first = first ? 1 : 0;
-        t.c_hi = c_hi; t.omc_hi = 1 - c_hi; t.c_lo = c_lo; t.omc_lo = 1 - c_lo;
-        LAUNCH("tail", l_tail, launch_tail(t, planes, ctx.stream));
-    }
     if (first && faithful)  // st.lowpassHi/Lo[levels] = residual (MagnifyCore.hpp:100-101)
     {
         const size_t n = (size_t)planes * lv[(size_t)levels].plane;
@@ -182,7 +161,7 @@ mc_status MotionMode::process(const ModeCtx& ctx, const FrameIO& io, const mc_pa
             return from_state ? BandSrc{hi[(size_t)l], lo[(size_t)l], gains[(size_t)l]} : BandSrc{M[(size_t)l], nullptr, 1.0f};
         };
         auto cur = [&](int l) { return l == levels - 1 ? band(l) : BandSrc{M[(size_t)l], nullptr, 1.0f}; };
-        for (int l = std::min(levels - 2, l_tail - 1); l >= 2; --l)   // the tail kernel has already produced cur_{l_tail}
+        for (int l = levels - 2; l >= 2; --l)
             LAUNCH("collapse", l, launch_collapse(lv[(size_t)l], lv[(size_t)l + 1], band(l), cur(l + 1), M[(size_t)l], planes, ctx.stream));
         m1 = band(1);
         if (levels >= 3) c2 = cur(2);

@@ -15,7 +15,7 @@ extern "C" const unsigned char _binary_lab_lut_s16_bin_end[];
 
 namespace mc {
 
-void build_lab_lut_packed(std::vector<LabLutEntry>& out) {
+void build_lab_lut_cells(std::vector<LabLutCell>& out) {
     const int n = kLabLutDim;
     const size_t bytes = (size_t)(_binary_lab_lut_s16_bin_end - _binary_lab_lut_s16_bin_start);
     if (bytes != (size_t)n * n * n * 3 * sizeof(int16_t)) {
@@ -24,18 +24,17 @@ void build_lab_lut_packed(std::vector<LabLutEntry>& out) {
     }
     std::vector<int16_t> raw((size_t)n * n * n * 3);
     std::memcpy(raw.data(), _binary_lab_lut_s16_bin_start, bytes);
-    out.assign((size_t)n * n * n, LabLutEntry{});
-    for (int b = 0; b < n; ++b)
+    out.assign((size_t)kLabLutCells, LabLutCell{});
+    for (int b = 0; b <= n; ++b)          // slab n repeats slab n-1 (only ever read with weight 0)
         for (int g = 0; g < n; ++g)
             for (int r = 0; r < n; ++r) {
-                const int r1 = std::min(r + 1, n - 1);
-                const int16_t* e0 = &raw[(((size_t)b * n + g) * n + r) * 3];
-                const int16_t* e1 = &raw[(((size_t)b * n + g) * n + r1) * 3];
-                LabLutEntry& e = out[((size_t)b * n + g) * n + r];
-                e.v[0] = e0[0]; e.v[1] = e1[0];   // L at r, r+1
-                e.v[2] = e0[1]; e.v[3] = e1[1];   // a
-                e.v[4] = e0[2]; e.v[5] = e1[2];   // b
-                e.v[6] = 0; e.v[7] = 0;
+                const int bb = std::min(b, n - 1), g1 = std::min(g + 1, n - 1), r1 = std::min(r + 1, n - 1);
+                LabLutCell& c = out[((size_t)b * n + g) * n + r];
+                const int gs[2] = {g, g1}, rs[2] = {r, r1};
+                for (int ig = 0; ig < 2; ++ig)
+                    for (int ch = 0; ch < 3; ++ch)
+                        for (int ir = 0; ir < 2; ++ir)
+                            c.v[6 * ig + 2 * ch + ir] = raw[((((size_t)bb * n + gs[ig]) * n + rs[ir]) * 3) + ch];
             }
 }
 

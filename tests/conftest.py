@@ -12,22 +12,8 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu under gpurun)")
     config.addinivalue_line("markers", "emu: kernel-logic check on the CUDA-on-CPU emulation (tests/cuda_emu), no GPU")
-    config.addinivalue_line("markers", "experimental: exercises an A/B kernel option that ships OFF and has only been "
-                            "verified on the CUDA emulation so far; runs under MC_EMU=1, or on a GPU with MC_EXPERIMENTAL=1")
     if os.environ.get("MC_EMU") == "1":
         use_emulated_library(asan=os.environ.get("MC_EMU_ASAN") == "1")
-
-
-def pytest_collection_modifyitems(config, items):
-    """Kernel options that ship off (prefetch_state, use_tail, ingest_compact) are verified on the emulation only until
-    their first B200 measurement; their tests do not gate the default GPU suite (`-x` would stop it at the first
-    surprise) — run them on hardware with MC_EXPERIMENTAL=1."""
-    if os.environ.get("MC_EMU") == "1" or os.environ.get("MC_EXPERIMENTAL") == "1":
-        return
-    skip = pytest.mark.skip(reason="off-by-default kernel option, emulation-verified only: set MC_EXPERIMENTAL=1 on a GPU")
-    for item in items:
-        if "experimental" in item.keywords:
-            item.add_marker(skip)
 
 
 def use_emulated_library(asan=False):

@@ -11,11 +11,11 @@ using namespace mc;
 
 namespace {
 struct Tables {
-    std::vector<LabLutEntry> lut;
+    std::vector<LabLutCell> lut;
     std::vector<float4> gam;
     LabInvCoeffs k;
     Tables() {
-        build_lab_lut_packed(lut);
+        build_lab_lut_cells(lut);
         build_inv_gamma_spline(gam);
         build_lab_inv_coeffs(k);
     }
