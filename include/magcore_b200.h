@@ -164,6 +164,8 @@ void* mc_stream(mc_handle* h);
  *   "prefetch_state" (default 1; needs use_tma): the fused level kernel requests the tile's two state planes as TMA
  *        bulk copies at kernel entry, together with its input window, instead of loading them in its last phase
  *        (same results; measured on B200: level[1] 235 -> 205 us per 32-lane launch; 0 kept for A/B measurements)
+ *   "egress_strip" (default 1): Laplace egress runs as the register/shuffle strip kernel (one warp per 128-column
+ *        strip, no shared memory); 0 selects the shared-memory tile kernel (bit-identical results; kept for A/B)
  *   "ingest_warps" (default 1): warps per CTA (1, 2 or 4) of the fused BGR->Lab ingest kernel (same results; A/B)
  *   "analysis_only" (default 0): Laplace and Phase — frames after the first update the temporal state (EMA planes;
  *        Riesz pyramids, phase accumulators and Butterworth registers) but skip synthesis and egress and report

@@ -680,6 +680,66 @@ struct EgressArgs {
     float* fout;
 };
 
+// The pixel stage of egress for the 4 output pixels (gy, gx .. gx+3) of stream `lane`: input (+ motion `up`, the a / b
+// planes attenuated by chroma) -> Lab2BGR -> u8 (MagnifyCore.hpp:140-158).
+template <int C>
+__device__ __forceinline__ void egress_pixels(const EgressArgs& a, int lane, int gy, int gx, const float (&up)[C][4]) {
+    uint8_t o8[4 * C];
+    float of[4 * C];
+    if (C == 3) {
+        const int16_t* lp = a.lab + (size_t)(lane * 3) * a.plane16 + (size_t)gy * a.pitch16 + gx;
+        const short4 qL = __ldg(reinterpret_cast<const short4*>(lp));
+        const short4 qA = __ldg(reinterpret_cast<const short4*>(lp + a.plane16));
+        const short4 qB = __ldg(reinterpret_cast<const short4*>(lp + 2 * a.plane16));
+        const short vL[4] = {qL.x, qL.y, qL.z, qL.w}, vA[4] = {qA.x, qA.y, qA.z, qA.w}, vB[4] = {qB.x, qB.y, qB.z, qB.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float L = (float)vL[i] * (100.0f / 16384.0f);
+            float A = fmaf((float)vA[i], 1.0f / 64.0f, -128.0f);
+            float B = fmaf((float)vB[i], 1.0f / 64.0f, -128.0f);
+            if (a.m1.a) {
+                // a,b motion planes *= chromAttenuation, then output = input + motion (MagnifyCore.hpp:140-148)
+                L = L + up[0][i];
+                A = A + up[C > 1 ? 1 : 0][i] * a.chroma;
+                B = B + up[C > 2 ? 2 : 0][i] * a.chroma;
+            }
+            float ob, og, orr;
+            lab_to_bgr_fast(L, A, B, a.coeffs, a.gtab, ob, og, orr);
+            of[3 * i] = ob; of[3 * i + 1] = og; of[3 * i + 2] = orr;
+            // lab_to_bgr clips to [0,1] before the gamma spline, so the saturating branches of
+            // convertTo reduce to a min with 255 (NaN -> 0 by the conversion itself)
+            o8[3 * i] = unit01_to_u8(ob); o8[3 * i + 1] = unit01_to_u8(og); o8[3 * i + 2] = unit01_to_u8(orr);
+        }
+    } else {
+        const uint8_t* p = a.in + (size_t)lane * a.in_lane_stride + (size_t)gy * a.in_step + gx;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float v = (gx + i < a.w0) ? u8_to_unit(__ldg(p + i)) : 0.0f;
+            if (a.m1.a) v = v + up[0][i];
+            of[i] = v;
+            o8[i] = unit_to_u8(v);
+        }
+    }
+    uint8_t* q = a.out + (size_t)lane * a.out_lane_stride + (size_t)gy * a.out_step + (size_t)gx * C;
+    const bool full = gx + 4 <= a.w0;
+    if (full && ((reinterpret_cast<uintptr_t>(q) & 3) == 0)) {
+#pragma unroll
+        for (int wd = 0; wd < C; ++wd)
+            reinterpret_cast<uint32_t*>(q)[wd] = (uint32_t)o8[4 * wd] | ((uint32_t)o8[4 * wd + 1] << 8) |
+                                                 ((uint32_t)o8[4 * wd + 2] << 16) | ((uint32_t)o8[4 * wd + 3] << 24);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4 * C; ++i)
+            if (gx + i / C < a.w0) q[i] = o8[i];
+    }
+    if (a.fout) {
+        float* f = a.fout + (((size_t)lane * a.h0 + gy) * a.w0 + gx) * C;
+#pragma unroll
+        for (int i = 0; i < 4 * C; ++i)
+            if (gx + i / C < a.w0) f[i] = of[i];
+    }
+}
+
 template <int C>
 __global__ void __launch_bounds__(256) k_egress(const EgressArgs a) {
     __shared__ __align__(16) float sC2[C][E2H][E2P];
@@ -698,6 +758,87 @@ __global__ void __launch_bounds__(256) k_egress(const EgressArgs a) {
         // when the level-2 window is loaded (entries hold s[upsrc(i)]).
         const bool has2 = a.c2.a != nullptr;
         const int bx2 = x0 / 4 - 2, by2 = y0 / 4 - 2;
+        const float g1 = a.m1.gain;
+        const bool from_state = a.m1.b != nullptr;
+        // Interior tiles (both windows inside their levels: no border rule to apply) build the windows with aligned
+        // 128-bit loads and fixed index arithmetic — a third of the instructions of the generic path below, which
+        // tiles touching an image border keep.  Same operations in the same order, bit-identical values.
+        const bool interior = blockIdx.x >= 1 && blockIdx.y >= 1 && x0 / 2 + 33 <= w1 && y0 / 2 + 17 <= h1 &&
+                              (!has2 || (x0 / 4 + 18 <= a.l2.w && y0 / 4 + 10 <= a.l2.h));
+        if (interior) {
+            if (has2) {
+                // level-2 window rows by2 .. by2+11, columns bx2 .. bx2+19, read as the aligned groups x2 = x0/4-4+4g
+                const bool st2 = a.c2.b != nullptr;
+                for (int i = threadIdx.x; i < C * E2H * 6; i += 256) {
+                    const int ch = i / (E2H * 6), r = i - ch * (E2H * 6);
+                    const int k = r / 6, g = r - k * 6;
+                    const size_t o2 = (size_t)(lane * C + ch) * a.l2.plane + (size_t)(by2 + k) * a.l2.pitch + (x0 / 4 - 4 + 4 * g);
+                    float4 v = __ldg(reinterpret_cast<const float4*>(a.c2.a + o2));
+                    if (st2) {
+                        const float4 u = __ldg(reinterpret_cast<const float4*>(a.c2.b + o2));
+                        v.x = (v.x - u.x) * a.c2.gain; v.y = (v.y - u.y) * a.c2.gain; v.z = (v.z - u.z) * a.c2.gain; v.w = (v.w - u.w) * a.c2.gain;
+                    }
+                    const int j = 4 * g - 2;
+                    float* d = &sC2[ch][k][0];
+                    if (g >= 1) { d[j] = v.x; d[j + 1] = v.y; }
+                    if (g <= 4) { d[j + 2] = v.z; d[j + 3] = v.w; }
+                }
+                __syncthreads();
+                // horizontal pyrUp of each window row at the 34 level-1 columns x0/2-1+j, two columns (odd, even) per item:
+                // x1 = x0/2-1+2p is odd -> (s[i] + s[i+1]) * 4, x1+1 is even -> s[i] + 6 s[i+1] + s[i+2], window index of i = p+1
+                for (int i = threadIdx.x; i < C * E2H * 17; i += 256) {
+                    const int ch = i / (E2H * 17), r = i - ch * (E2H * 17);
+                    const int ky = r / 17, p = r - ky * 17;
+                    const float s0 = sC2[ch][ky][p + 1], s1 = sC2[ch][ky][p + 2], s2 = sC2[ch][ky][p + 3];
+                    float2 o;
+                    o.x = (s0 + s1) * 4.0f;
+                    o.y = s0 + s1 * 6.0f + s2;
+                    *reinterpret_cast<float2*>(&sT[ch][ky][2 * p]) = o;
+                }
+                __syncthreads();
+            }
+            // level-1 window rows y0/2-1+k: columns j = 1 .. 32 as eight aligned groups of four (x1 = x0/2+4g), then the
+            // two edge columns j = 0 and j = 33 one value at a time
+            for (int i = threadIdx.x; i < C * DH * 8 + C * DH * 2; i += 256) {
+                const bool grp = i < C * DH * 8;
+                const int ii = grp ? i : i - C * DH * 8;
+                const int per = grp ? DH * 8 : DH * 2;
+                const int ch = ii / per, r = ii - ch * per;
+                const int k = grp ? r >> 3 : r >> 1, g = grp ? r & 7 : r & 1;
+                const int j0 = grp ? 4 * g + 1 : 33 * g;
+                const size_t o1 = (size_t)(lane * C + ch) * a.l1.plane + (size_t)(y0 / 2 - 1 + k) * a.l1.pitch + (x0 / 2 - 1 + j0);
+                const int ky = ((k - 1) >> 1) + 2;        // window row of level-2 pixel y1 >> 1, y1 = y0/2-1+k
+                const bool odd = !(k & 1);                // y1 odd <=> k even (y0/2 is even)
+                if (grp) {
+                    const float4 hv = __ldg(reinterpret_cast<const float4*>(a.m1.a + o1));
+                    float v[4] = {hv.x, hv.y, hv.z, hv.w};
+                    if (from_state) {
+                        const float4 lv4 = __ldg(reinterpret_cast<const float4*>(a.m1.b + o1));
+                        v[0] = (v[0] - lv4.x) * g1; v[1] = (v[1] - lv4.y) * g1; v[2] = (v[2] - lv4.z) * g1; v[3] = (v[3] - lv4.w) * g1;
+                    }
+                    if (has2) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float r0 = sT[ch][ky - 1][j0 + e], r1 = sT[ch][ky][j0 + e], r2 = sT[ch][ky + 1][j0 + e];
+                            const float ue = (r0 + r1 * 6.0f + r2) * kInv64, uo = ((r1 + r2) * 4.0f) * kInv64;
+                            v[e] = (odd ? uo : ue) + v[e];
+                        }
+                    }
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) sD[ch][k][j0 + e] = v[e];
+                } else {
+                    float v = __ldg(a.m1.a + o1);
+                    if (from_state) v = (v - __ldg(a.m1.b + o1)) * g1;
+                    if (has2) {
+                        const float r0 = sT[ch][ky - 1][j0], r1 = sT[ch][ky][j0], r2 = sT[ch][ky + 1][j0];
+                        const float ue = (r0 + r1 * 6.0f + r2) * kInv64, uo = ((r1 + r2) * 4.0f) * kInv64;
+                        v = (odd ? uo : ue) + v;
+                    }
+                    sD[ch][k][j0] = v;
+                }
+            }
+            __syncthreads();
+        } else {
         if (has2) {
             {
                 const size_t base2 = (size_t)(lane * C) * a.l2.plane;
@@ -730,8 +871,6 @@ __global__ void __launch_bounds__(256) k_egress(const EgressArgs a) {
             ph[ch] = a.m1.a + (size_t)(lane * C + ch) * a.l1.plane;
             pl[ch] = a.m1.b ? a.m1.b + (size_t)(lane * C + ch) * a.l1.plane : nullptr;
         }
-        const float g1 = a.m1.gain;
-        const bool from_state = a.m1.b != nullptr;
         for (int i = threadIdx.x; i < DH * DW; i += 256) {
             const int k = i / DW, j = i - k * DW;
             const int y1 = upsrc(y0 / 2 - 1 + k, h1), x1 = upsrc(x0 / 2 - 1 + j, w1);
@@ -756,6 +895,7 @@ __global__ void __launch_bounds__(256) k_egress(const EgressArgs a) {
             for (int ch = 0; ch < C; ++ch) sD[ch][k][j] = v[ch];
         }
         __syncthreads();
+        }
     }
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const int gx = x0 + 4 * tx;
@@ -785,60 +925,172 @@ __global__ void __launch_bounds__(256) k_egress(const EgressArgs a) {
     for (int ry = 0; ry < 2; ++ry) {
         const int gy = y0 + 2 * ty + ry;
         if (gy >= a.h0) continue;
-        uint8_t o8[4 * C];
-        float of[4 * C];
-        if (C == 3) {
-            const int16_t* lp = a.lab + (size_t)(lane * 3) * a.plane16 + (size_t)gy * a.pitch16 + gx;
-            const short4 qL = __ldg(reinterpret_cast<const short4*>(lp));
-            const short4 qA = __ldg(reinterpret_cast<const short4*>(lp + a.plane16));
-            const short4 qB = __ldg(reinterpret_cast<const short4*>(lp + 2 * a.plane16));
-            const short vL[4] = {qL.x, qL.y, qL.z, qL.w}, vA[4] = {qA.x, qA.y, qA.z, qA.w}, vB[4] = {qB.x, qB.y, qB.z, qB.w};
+        float upr[C][4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                float L = (float)vL[i] * (100.0f / 16384.0f);
-                float A = fmaf((float)vA[i], 1.0f / 64.0f, -128.0f);
-                float B = fmaf((float)vB[i], 1.0f / 64.0f, -128.0f);
-                if (a.m1.a) {
-                    // a,b motion planes *= chromAttenuation, then output = input + motion (MagnifyCore.hpp:140-148)
-                    L = L + up[0][ry][i];
-                    A = A + up[C > 1 ? 1 : 0][ry][i] * a.chroma;
-                    B = B + up[C > 2 ? 2 : 0][ry][i] * a.chroma;
+        for (int ch = 0; ch < C; ++ch)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) upr[ch][i] = up[ch][ry][i];
+        egress_pixels<C>(a, lane, gy, gx, upr);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// egress, strip form (default): the same collapse of levels 2 -> 1 -> 0 and pixel stage as k_egress, without shared
+// memory, barriers or per-position index arithmetic.  One warp owns a strip of 128 output columns (lane = 4 columns =
+// 2 level-1 columns = 1 level-2 column; lanes 0 and 31 only provide the halo, strips advance by 120 columns) and walks
+// EG_ROWS output rows top to bottom: horizontal pyrUp passes take their neighbours from the adjacent lanes by shuffle,
+// vertical passes are register sliding windows — three horizontally expanded level-2 rows (H2) and three horizontally
+// expanded cur_1 rows (E).  Every value is computed by the same operations in the same order as in k_egress (and as
+// cv::pyrUp: row pass first), so the two kernels agree bit for bit; pyrUp's border rule (s[-1] := s[1],
+// s[n] := s[n-1]) is applied to the shuffled / streamed neighbours.  The kernel is issue-bound (Lab2BGR), not HBM-bound.
+// ------------------------------------------------------------------------------------------------
+constexpr int EG_ROWS = 64;   // output rows per warp (a multiple of 4)
+
+template <int C>
+__global__ void __launch_bounds__(32) k_egress_strip(const EgressArgs a) {
+    const unsigned full = 0xffffffffu;
+    const int lane_id = threadIdx.x;
+    const int lane = blockIdx.z;
+    const int gx = blockIdx.x * DS_COLS - 4 + lane_id * 4;          // first output column of this lane (multiple of 4)
+    const int f0 = blockIdx.y * EG_ROWS;
+    if (f0 >= a.h0) return;
+    const int f_end = min(f0 + EG_ROWS, a.h0);
+    const bool px_owner = lane_id >= 1 && lane_id <= 30 && gx < a.w0;
+    if (!a.m1.a) {   // no motion (first frame, or fewer than two levels): conversion only
+        float zero[C][4];
+#pragma unroll
+        for (int ch = 0; ch < C; ++ch)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) zero[ch][i] = 0.0f;
+        if (px_owner)
+            for (int gy = f0; gy < f_end; ++gy) egress_pixels<C>(a, lane, gy, gx, zero);
+        return;
+    }
+    const int w1 = a.l1.w, h1 = a.l1.h, w2 = a.l2.w, h2 = a.l2.h;
+    const int x1a = gx >> 1, x2 = gx >> 2;                           // lane 0 of strip 0: -2, -1
+    const bool has2 = a.c2.a != nullptr, from_state = a.m1.b != nullptr;
+    const float g1 = a.m1.gain;
+    // clamped columns for the loads of lanes outside the level (their values are never used)
+    const int x1l = x1a < 0 ? 0 : (x1a >= w1 ? ((w1 - 1) & ~1) : x1a);
+    const int x2l = x2 < 0 ? 0 : (x2 >= w2 ? w2 - 1 : x2);
+    const int x2r = x2l + 1 >= w2 ? w2 - 1 : x2l + 1;                // lane 31's right neighbour column
+    size_t base1[C], base2[C];
+#pragma unroll
+    for (int ch = 0; ch < C; ++ch) {
+        base1[ch] = (size_t)(lane * C + ch) * a.l1.plane + x1l;
+        base2[ch] = (size_t)(lane * C + ch) * a.l2.plane;
+    }
+
+    // H2 window: horizontally expanded level-2 rows (i-1, i, i+1) at the lane's two level-1 columns (even, odd)
+    float hA[C][2], hB[C][2], hC[C][2];
+#pragma unroll
+    for (int ch = 0; ch < C; ++ch) hA[ch][0] = hA[ch][1] = hB[ch][0] = hB[ch][1] = hC[ch][0] = hC[ch][1] = 0.0f;
+    auto load_h2 = [&](int y2, float (&h)[C][2]) {
+        const size_t ro = (size_t)upsrc(y2, h2) * a.l2.pitch;
+#pragma unroll
+        for (int ch = 0; ch < C; ++ch) {
+            const float v = band_at(a.c2, base2[ch] + ro + x2l);
+            float l = __shfl_up_sync(full, v, 1), r = __shfl_down_sync(full, v, 1);
+            if (lane_id == 31) r = band_at(a.c2, base2[ch] + ro + x2r);
+            if (x2 == 0) l = r;                    // s[-1] := s[1]
+            if (x2 + 1 >= w2) r = v;               // s[w2] := s[w2-1]
+            h[ch][0] = l + v * 6.0f + r;
+            h[ch][1] = (v + r) * 4.0f;
+        }
+    };
+    // cur_1 row y1 (inside the level) at the lane's two columns = pyrUp(cur_2) + m_1, then its horizontal expansion
+    // at the lane's four output columns.  `odd`: y1 odd -> level-2 rows (p, q) only.
+    auto cur1_row = [&](int y1, bool odd, const float (&p)[C][2], const float (&q)[C][2], const float (&r)[C][2], float (&E)[C][4]) {
+        const size_t ro = (size_t)y1 * a.l1.pitch;
+#pragma unroll
+        for (int ch = 0; ch < C; ++ch) {
+            const float2 hv = __ldg(reinterpret_cast<const float2*>(a.m1.a + base1[ch] + ro));
+            float ca = hv.x, cb = hv.y;
+            if (from_state) {
+                const float2 lv2 = __ldg(reinterpret_cast<const float2*>(a.m1.b + base1[ch] + ro));
+                ca = (ca - lv2.x) * g1;
+                cb = (cb - lv2.y) * g1;
+            }
+            if (has2) {
+                const float ua = odd ? ((p[ch][0] + q[ch][0]) * 4.0f) * kInv64 : (p[ch][0] + q[ch][0] * 6.0f + r[ch][0]) * kInv64;
+                const float ub = odd ? ((p[ch][1] + q[ch][1]) * 4.0f) * kInv64 : (p[ch][1] + q[ch][1] * 6.0f + r[ch][1]) * kInv64;
+                ca = ua + ca;
+                cb = ub + cb;
+            }
+            if (x1a + 1 >= w1) cb = ca;                                  // cur_1[w1] := cur_1[w1-1]
+            float left = __shfl_up_sync(full, cb, 1), right = __shfl_down_sync(full, ca, 1);
+            if (x1a == 0) left = cb;                                     // cur_1[-1] := cur_1[1]
+            if (x1a + 2 >= w1) right = cb;
+            E[ch][0] = left + ca * 6.0f + cb;
+            E[ch][1] = (ca + cb) * 4.0f;
+            E[ch][2] = ca + cb * 6.0f + right;
+            E[ch][3] = (cb + right) * 4.0f;
+        }
+    };
+
+    const int j0 = f0 >> 1;                       // first level-1 row of the chunk (even)
+    float Em[C][4], E0[C][4], Ep[C][4];
+    if (has2) {
+        const int ic = j0 >> 1;
+        load_h2(ic - 1, hA);
+        load_h2(ic, hB);
+        load_h2(ic + 1, hC);
+    }
+    if (j0 > 0) cur1_row(j0 - 1, true, hA, hB, hC, Em);      // odd row of the previous window centre: level-2 rows (ic-1, ic)
+    else {
+#pragma unroll
+        for (int ch = 0; ch < C; ++ch)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) Em[ch][i] = 0.0f;    // replaced by row 1 below
+    }
+    cur1_row(j0, false, hA, hB, hC, E0);
+    const int j_end = (f_end + 1) >> 1;
+    for (int j = j0; j < j_end; ++j) {
+        // row j+1 of cur_1 (or its border copy) -> Ep
+        const int jn = j + 1;
+        if (jn >= h1) {
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) Ep[ch][i] = E0[ch][i];
+        } else if (jn & 1) {
+            cur1_row(jn, true, hB, hC, hC, Ep);              // odd: level-2 rows (i, i+1) of the current centre
+        } else {
+            if (has2) {                                      // slide the level-2 window to centre jn / 2
+#pragma unroll
+                for (int ch = 0; ch < C; ++ch) {
+                    hA[ch][0] = hB[ch][0]; hA[ch][1] = hB[ch][1];
+                    hB[ch][0] = hC[ch][0]; hB[ch][1] = hC[ch][1];
                 }
-                float ob, og, orr;
-                lab_to_bgr_fast(L, A, B, a.coeffs, a.gtab, ob, og, orr);
-                of[3 * i] = ob; of[3 * i + 1] = og; of[3 * i + 2] = orr;
-                // lab_to_bgr clips to [0,1] before the gamma spline, so the saturating branches of
-                // convertTo reduce to a min with 255 (NaN -> 0 by the conversion itself)
-                o8[3 * i] = unit01_to_u8(ob); o8[3 * i + 1] = unit01_to_u8(og); o8[3 * i + 2] = unit01_to_u8(orr);
+                load_h2((jn >> 1) + 1, hC);
             }
-        } else {
-            const uint8_t* p = a.in + (size_t)lane * a.in_lane_stride + (size_t)gy * a.in_step + gx;
+            cur1_row(jn, false, hA, hB, hC, Ep);
+        }
+        if (j == 0) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                float v = (gx + i < a.w0) ? u8_to_unit(__ldg(p + i)) : 0.0f;
-                if (a.m1.a) v = v + up[0][ry][i];
-                of[i] = v;
-                o8[i] = unit_to_u8(v);
+            for (int ch = 0; ch < C; ++ch)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) Em[ch][i] = Ep[ch][i];       // cur_1[-1] := cur_1[1]
+        }
+        if (px_owner) {
+            float up[C][4];
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) up[ch][i] = (Em[ch][i] + E0[ch][i] * 6.0f + Ep[ch][i]) * kInv64;
+            egress_pixels<C>(a, lane, 2 * j, gx, up);
+            if (2 * j + 1 < f_end) {
+#pragma unroll
+                for (int ch = 0; ch < C; ++ch)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) up[ch][i] = ((E0[ch][i] + Ep[ch][i]) * 4.0f) * kInv64;
+                egress_pixels<C>(a, lane, 2 * j + 1, gx, up);
             }
         }
-        uint8_t* q = a.out + (size_t)lane * a.out_lane_stride + (size_t)gy * a.out_step + (size_t)gx * C;
-        const bool full = gx + 4 <= a.w0;
-        if (full && ((reinterpret_cast<uintptr_t>(q) & 3) == 0)) {
 #pragma unroll
-            for (int wd = 0; wd < C; ++wd)
-                reinterpret_cast<uint32_t*>(q)[wd] = (uint32_t)o8[4 * wd] | ((uint32_t)o8[4 * wd + 1] << 8) |
-                                                     ((uint32_t)o8[4 * wd + 2] << 16) | ((uint32_t)o8[4 * wd + 3] << 24);
-        } else {
+        for (int ch = 0; ch < C; ++ch)
 #pragma unroll
-            for (int i = 0; i < 4 * C; ++i)
-                if (gx + i / C < a.w0) q[i] = o8[i];
-        }
-        if (a.fout) {
-            float* f = a.fout + (((size_t)lane * a.h0 + gy) * a.w0 + gx) * C;
-#pragma unroll
-            for (int i = 0; i < 4 * C; ++i)
-                if (gx + i / C < a.w0) f[i] = of[i];
-        }
+            for (int i = 0; i < 4; ++i) { Em[ch][i] = E0[ch][i]; E0[ch][i] = Ep[ch][i]; }
     }
 }
 
@@ -951,7 +1203,7 @@ cudaError_t launch_collapse(const Level& lf, const Level& lc, const BandSrc& fin
 
 cudaError_t launch_egress(const FrameIO& io, const DeviceTables& tb, const int16_t* lab, int pitch16, size_t plane16,
                           const BandSrc& m1, const Level& l1, const BandSrc& c2, const Level& l2, float chroma,
-                          float* fout, cudaStream_t s) {
+                          float* fout, cudaStream_t s, bool strip) {
     EgressArgs a;
     a.in = io.in; a.in_step = io.in_step; a.in_lane_stride = io.in_lane_stride;
     a.lab = lab; a.pitch16 = pitch16; a.plane16 = plane16;
@@ -959,9 +1211,15 @@ cudaError_t launch_egress(const FrameIO& io, const DeviceTables& tb, const int16
     a.w0 = io.w; a.h0 = io.h;
     a.gtab = tb.inv_gamma; a.coeffs = tb.inv_coeffs;
     a.m1 = m1; a.l1 = l1; a.c2 = c2; a.l2 = l2; a.chroma = chroma; a.fout = fout;
-    dim3 grid(cdiv(io.w, TW), cdiv(io.h, TH), io.lanes);
-    if (io.channels == 3) k_egress<3><<<grid, 256, 0, s>>>(a);
-    else k_egress<1><<<grid, 256, 0, s>>>(a);
+    if (strip) {
+        dim3 grid(cdiv(io.w, DS_COLS), cdiv(io.h, EG_ROWS), io.lanes);
+        if (io.channels == 3) k_egress_strip<3><<<grid, 32, 0, s>>>(a);
+        else k_egress_strip<1><<<grid, 32, 0, s>>>(a);
+    } else {
+        dim3 grid(cdiv(io.w, TW), cdiv(io.h, TH), io.lanes);
+        if (io.channels == 3) k_egress<3><<<grid, 256, 0, s>>>(a);
+        else k_egress<1><<<grid, 256, 0, s>>>(a);
+    }
     return cudaGetLastError();
 }
 

@@ -169,7 +169,7 @@ mc_status MotionMode::process(const ModeCtx& ctx, const FrameIO& io, const mc_pa
     const Level& l1 = lv[levels >= 1 ? 1 : 0];
     const Level& l2 = lv[levels >= 2 ? 2 : 0];
     LAUNCH("egress", 0, launch_egress(io, *ctx.tables, lab16, pitch16, plane16, m1, l1, c2, l2, (float)p.chromAttenuation, ctx.float_out,
-                                      ctx.stream));
+                                      ctx.stream, ctx.egress_strip));
     empty = false;
     *produced = 1;
     return MC_OK;

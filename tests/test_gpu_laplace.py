@@ -348,7 +348,8 @@ def test_prefetch_state_option_equals_default():
 
 
 @pytest.mark.parametrize("opts", [{"prefetch_state": 0}, {"band_from_state": 0}, {"prefetch_state": 0, "band_from_state": 0},
-                                  {"use_tma": 0}, {"ingest_warps": 2, "band_from_state": 0}, {"ingest_warps": 4}])
+                                  {"use_tma": 0}, {"ingest_warps": 2, "band_from_state": 0}, {"ingest_warps": 4},
+                                  {"egress_strip": 0}, {"egress_strip": 0, "band_from_state": 0}])
 def test_option_combinations_agree_with_default(opts):
     """The A/B options compose: any combination gives the default path's frames bit for bit, over the first frame,
     ragged borders and a parameter change."""
@@ -362,6 +363,28 @@ def test_option_combinations_agree_with_default(opts):
         _, oa = a.process_image(f, cfg)
         _, ob = b.process_image(f, cfg)
         assert int(u8_diff(oa, ob).max()) == 0, (opts, t)
+
+
+@pytest.mark.parametrize("w,h,c,lv", [(640, 480, 3, 4), (333, 251, 3, 5), (121, 75, 3, 3), (119, 64, 3, 3), (240, 67, 3, 2), (242, 130, 1, 3),
+                                      (250, 131, 3, 2), (64, 48, 1, 2), (481, 270, 3, 6), (126, 129, 3, 3)])
+def test_strip_egress_equals_tile_egress(w, h, c, lv):
+    """The register/shuffle strip egress kernel (default) and the shared-memory tile kernel (option egress_strip = 0)
+    collapse levels 2 -> 1 -> 0 with the same operations in the same order: bit-identical u8 frames and float taps,
+    over ragged strips and chunks (widths around 120, heights around 64), 2-level pyramids (no level-2 window), gray
+    frames, the first (no-motion) frame and both band sources."""
+    for band_from_state in (1, 0):
+        cfg, _ = make_cfgs(O.MODE_LAPLACE, 20, 50.0, 0.4, 3.0, 30, lv)
+        a, b = L.MagnificationProcessor(0), L.MagnificationProcessor(0)
+        for p in (a, b):
+            p.set_option("band_from_state", band_from_state)
+            p.set_option("keep_float_output", 1)
+        b.set_option("egress_strip", 0)
+        for t in range(4):
+            f = synth_frame(t, w, h, c)
+            _, oa = a.process_image(f, cfg)
+            _, ob = b.process_image(f, cfg)
+            assert np.array_equal(oa, ob), (w, h, t, band_from_state, int(u8_diff(oa, ob).max()))
+            assert np.array_equal(a.float_output(w, h, c), b.float_output(w, h, c)), (w, h, t)
 
 
 def test_ingest_warps_option_equals_default():
