@@ -67,6 +67,13 @@ __device__ __forceinline__ float down5(float a, float b, float c, float d, float
     return c * 6.0f + (b + d) * 4.0f + a + e;
 }
 
+// cv::pyrUp taps of the synthesis kernels (collapse, both egress forms).  The rounding is pinned with intrinsics — the
+// 6-tap term as one FMA, which is what nvcc contracts it to anyway — so that every kernel evaluating the same tap gives
+// the same bits whatever the surrounding code looks like (the strip and tile egress kernels are tested bit-identical).
+__device__ __forceinline__ float up3(float a, float b, float c) { return __fadd_rn(__fmaf_rn(b, 6.0f, a), c); }   // a + 6 b + c
+__device__ __forceinline__ float up2(float a, float b) { return __fmul_rn(__fadd_rn(a, b), 4.0f); }               // (a + b) * 4
+__device__ __forceinline__ float band_of(float hi, float lo, float gain) { return __fmul_rn(__fsub_rn(hi, lo), gain); }
+
 // ------------------------------------------------------------------------------------------------
 // lab16: pointwise, 4 pixels per thread (12 input bytes = three 32-bit words).
 // ------------------------------------------------------------------------------------------------
@@ -607,7 +614,7 @@ __global__ void __launch_bounds__(32 * WARPS) k_ingest_lab(const IngestArgs a) {
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float band_at(const BandSrc& b, size_t off) {
     const float v = __ldg(b.a + off);
-    return b.b ? (v - __ldg(b.b + off)) * b.gain : v;
+    return b.b ? band_of(v, __ldg(b.b + off), b.gain) : v;
 }
 
 __global__ void __launch_bounds__(256) k_collapse(Level lf, Level lc, BandSrc fine, BandSrc coarse, float* out) {
@@ -629,10 +636,10 @@ __global__ void __launch_bounds__(256) k_collapse(Level lf, Level lc, BandSrc fi
     for (int q = 0; q < 3; ++q) {
         const float2 p0 = *reinterpret_cast<const float2*>(&sD[ty + q][2 * tx]);
         const float2 p1 = *reinterpret_cast<const float2*>(&sD[ty + q][2 * tx + 2]);
-        e[q][0] = p0.x + p0.y * 6.0f + p1.x;
-        e[q][1] = (p0.y + p1.x) * 4.0f;
-        e[q][2] = p0.y + p1.x * 6.0f + p1.y;
-        e[q][3] = (p1.x + p1.y) * 4.0f;
+        e[q][0] = up3(p0.x, p0.y, p1.x);
+        e[q][1] = up2(p0.y, p1.x);
+        e[q][2] = up3(p0.y, p1.x, p1.y);
+        e[q][3] = up2(p1.x, p1.y);
     }
     const size_t fbase = (size_t)plane * lf.plane;
 #pragma unroll
@@ -643,18 +650,18 @@ __global__ void __launch_bounds__(256) k_collapse(Level lf, Level lc, BandSrc fi
         float4 v = *reinterpret_cast<const float4*>(fine.a + o);   // plain load: `out` may be this very plane
         if (fine.b) {
             const float4 u = __ldg(reinterpret_cast<const float4*>(fine.b + o));
-            v.x = (v.x - u.x) * fine.gain; v.y = (v.y - u.y) * fine.gain; v.z = (v.z - u.z) * fine.gain; v.w = (v.w - u.w) * fine.gain;
+            v.x = band_of(v.x, u.x, fine.gain); v.y = band_of(v.y, u.y, fine.gain); v.z = band_of(v.z, u.z, fine.gain); v.w = band_of(v.w, u.w, fine.gain);
         }
         if (ry == 0) {
-            v.x = (e[0][0] + e[1][0] * 6.0f + e[2][0]) * kInv64 + v.x;
-            v.y = (e[0][1] + e[1][1] * 6.0f + e[2][1]) * kInv64 + v.y;
-            v.z = (e[0][2] + e[1][2] * 6.0f + e[2][2]) * kInv64 + v.z;
-            v.w = (e[0][3] + e[1][3] * 6.0f + e[2][3]) * kInv64 + v.w;
+            v.x = __fmaf_rn(up3(e[0][0], e[1][0], e[2][0]), kInv64, v.x);   // * 2^-6 is exact: one rounding, in the add
+            v.y = __fmaf_rn(up3(e[0][1], e[1][1], e[2][1]), kInv64, v.y);
+            v.z = __fmaf_rn(up3(e[0][2], e[1][2], e[2][2]), kInv64, v.z);
+            v.w = __fmaf_rn(up3(e[0][3], e[1][3], e[2][3]), kInv64, v.w);
         } else {
-            v.x = ((e[1][0] + e[2][0]) * 4.0f) * kInv64 + v.x;
-            v.y = ((e[1][1] + e[2][1]) * 4.0f) * kInv64 + v.y;
-            v.z = ((e[1][2] + e[2][2]) * 4.0f) * kInv64 + v.z;
-            v.w = ((e[1][3] + e[2][3]) * 4.0f) * kInv64 + v.w;
+            v.x = __fmaf_rn(up2(e[1][0], e[2][0]), kInv64, v.x);
+            v.y = __fmaf_rn(up2(e[1][1], e[2][1]), kInv64, v.y);
+            v.z = __fmaf_rn(up2(e[1][2], e[2][2]), kInv64, v.z);
+            v.w = __fmaf_rn(up2(e[1][3], e[2][3]), kInv64, v.w);
         }
         *reinterpret_cast<float4*>(out + o) = v;
     }
@@ -681,63 +688,108 @@ struct EgressArgs {
 };
 
 // The pixel stage of egress for the 4 output pixels (gy, gx .. gx+3) of stream `lane`: input (+ motion `up`, the a / b
-// planes attenuated by chroma) -> Lab2BGR -> u8 (MagnifyCore.hpp:140-158).
+// planes attenuated by chroma) -> Lab2BGR -> u8 (MagnifyCore.hpp:140-158).  Split into the load of the input samples
+// (so that the strip kernel can request them an iteration ahead) and the conversion.
+template <int C> struct EgressIn;
+template <> struct EgressIn<3> { short4 L, A, B; };
+template <> struct EgressIn<1> { uint32_t g; };
+
 template <int C>
-__device__ __forceinline__ void egress_pixels(const EgressArgs& a, int lane, int gy, int gx, const float (&up)[C][4]) {
-    uint8_t o8[4 * C];
-    float of[4 * C];
-    if (C == 3) {
-        const int16_t* lp = a.lab + (size_t)(lane * 3) * a.plane16 + (size_t)gy * a.pitch16 + gx;
-        const short4 qL = __ldg(reinterpret_cast<const short4*>(lp));
-        const short4 qA = __ldg(reinterpret_cast<const short4*>(lp + a.plane16));
-        const short4 qB = __ldg(reinterpret_cast<const short4*>(lp + 2 * a.plane16));
-        const short vL[4] = {qL.x, qL.y, qL.z, qL.w}, vA[4] = {qA.x, qA.y, qA.z, qA.w}, vB[4] = {qB.x, qB.y, qB.z, qB.w};
+__device__ __forceinline__ EgressIn<C> egress_load(const EgressArgs& a, int lane, int gy, int gx);
+template <>
+__device__ __forceinline__ EgressIn<3> egress_load<3>(const EgressArgs& a, int lane, int gy, int gx) {
+    const int16_t* lp = a.lab + (size_t)(lane * 3) * a.plane16 + (size_t)gy * a.pitch16 + gx;
+    EgressIn<3> r;
+    r.L = __ldg(reinterpret_cast<const short4*>(lp));
+    r.A = __ldg(reinterpret_cast<const short4*>(lp + a.plane16));
+    r.B = __ldg(reinterpret_cast<const short4*>(lp + 2 * a.plane16));
+    return r;
+}
+template <>
+__device__ __forceinline__ EgressIn<1> egress_load<1>(const EgressArgs& a, int lane, int gy, int gx) {
+    const uint8_t* p = a.in + (size_t)lane * a.in_lane_stride + (size_t)gy * a.in_step + gx;
+    EgressIn<1> r;
+    r.g = 0;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            float L = (float)vL[i] * (100.0f / 16384.0f);
-            float A = fmaf((float)vA[i], 1.0f / 64.0f, -128.0f);
-            float B = fmaf((float)vB[i], 1.0f / 64.0f, -128.0f);
-            if (a.m1.a) {
-                // a,b motion planes *= chromAttenuation, then output = input + motion (MagnifyCore.hpp:140-148)
-                L = L + up[0][i];
-                A = A + up[C > 1 ? 1 : 0][i] * a.chroma;
-                B = B + up[C > 2 ? 2 : 0][i] * a.chroma;
-            }
-            float ob, og, orr;
-            lab_to_bgr_fast(L, A, B, a.coeffs, a.gtab, ob, og, orr);
-            of[3 * i] = ob; of[3 * i + 1] = og; of[3 * i + 2] = orr;
-            // lab_to_bgr clips to [0,1] before the gamma spline, so the saturating branches of
-            // convertTo reduce to a min with 255 (NaN -> 0 by the conversion itself)
-            o8[3 * i] = unit01_to_u8(ob); o8[3 * i + 1] = unit01_to_u8(og); o8[3 * i + 2] = unit01_to_u8(orr);
-        }
-    } else {
-        const uint8_t* p = a.in + (size_t)lane * a.in_lane_stride + (size_t)gy * a.in_step + gx;
+    for (int i = 0; i < 4; ++i)
+        if (gx + i < a.w0) r.g |= (uint32_t)__ldg(p + i) << (8 * i);
+    return r;
+}
+
+template <int C>
+__device__ __forceinline__ void egress_convert(const EgressArgs& a, int lane, int gy, int gx, const EgressIn<C>& in, const float (&up)[C][4]);
+template <>
+__device__ __forceinline__ void egress_convert<3>(const EgressArgs& a, int lane, int gy, int gx, const EgressIn<3>& in, const float (&up)[3][4]) {
+    uint8_t o8[12];
+    float of[12];
+    const short vL[4] = {in.L.x, in.L.y, in.L.z, in.L.w}, vA[4] = {in.A.x, in.A.y, in.A.z, in.A.w}, vB[4] = {in.B.x, in.B.y, in.B.z, in.B.w};
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            float v = (gx + i < a.w0) ? u8_to_unit(__ldg(p + i)) : 0.0f;
-            if (a.m1.a) v = v + up[0][i];
-            of[i] = v;
-            o8[i] = unit_to_u8(v);
+    for (int i = 0; i < 4; ++i) {
+        float L = (float)vL[i] * (100.0f / 16384.0f);
+        float A = fmaf((float)vA[i], 1.0f / 64.0f, -128.0f);
+        float B = fmaf((float)vB[i], 1.0f / 64.0f, -128.0f);
+        if (a.m1.a) {
+            // a,b motion planes *= chromAttenuation, then output = input + motion (MagnifyCore.hpp:140-148)
+            L = __fadd_rn(L, up[0][i]);
+            A = __fadd_rn(A, __fmul_rn(up[1][i], a.chroma));   // the reference scales the plane, then adds
+            B = __fadd_rn(B, __fmul_rn(up[2][i], a.chroma));
         }
+        float ob, og, orr;
+        lab_to_bgr_fast(L, A, B, a.coeffs, a.gtab, ob, og, orr);
+        of[3 * i] = ob; of[3 * i + 1] = og; of[3 * i + 2] = orr;
+        // lab_to_bgr clips to [0,1] before the gamma spline, so the saturating branches of
+        // convertTo reduce to a min with 255 (NaN -> 0 by the conversion itself)
+        o8[3 * i] = unit01_to_u8(ob); o8[3 * i + 1] = unit01_to_u8(og); o8[3 * i + 2] = unit01_to_u8(orr);
     }
-    uint8_t* q = a.out + (size_t)lane * a.out_lane_stride + (size_t)gy * a.out_step + (size_t)gx * C;
-    const bool full = gx + 4 <= a.w0;
-    if (full && ((reinterpret_cast<uintptr_t>(q) & 3) == 0)) {
+    uint8_t* q = a.out + (size_t)lane * a.out_lane_stride + (size_t)gy * a.out_step + (size_t)gx * 3;
+    if (gx + 4 <= a.w0 && ((reinterpret_cast<uintptr_t>(q) & 3) == 0)) {
 #pragma unroll
-        for (int wd = 0; wd < C; ++wd)
+        for (int wd = 0; wd < 3; ++wd)
             reinterpret_cast<uint32_t*>(q)[wd] = (uint32_t)o8[4 * wd] | ((uint32_t)o8[4 * wd + 1] << 8) |
                                                  ((uint32_t)o8[4 * wd + 2] << 16) | ((uint32_t)o8[4 * wd + 3] << 24);
     } else {
 #pragma unroll
-        for (int i = 0; i < 4 * C; ++i)
-            if (gx + i / C < a.w0) q[i] = o8[i];
+        for (int i = 0; i < 12; ++i)
+            if (gx + i / 3 < a.w0) q[i] = o8[i];
     }
     if (a.fout) {
-        float* f = a.fout + (((size_t)lane * a.h0 + gy) * a.w0 + gx) * C;
+        float* f = a.fout + (((size_t)lane * a.h0 + gy) * a.w0 + gx) * 3;
 #pragma unroll
-        for (int i = 0; i < 4 * C; ++i)
-            if (gx + i / C < a.w0) f[i] = of[i];
+        for (int i = 0; i < 12; ++i)
+            if (gx + i / 3 < a.w0) f[i] = of[i];
     }
+}
+template <>
+__device__ __forceinline__ void egress_convert<1>(const EgressArgs& a, int lane, int gy, int gx, const EgressIn<1>& in, const float (&up)[1][4]) {
+    uint8_t o8[4];
+    float of[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float v = u8_to_unit((uint8_t)((in.g >> (8 * i)) & 0xff));
+        if (a.m1.a) v = __fadd_rn(v, up[0][i]);
+        of[i] = v;
+        o8[i] = unit_to_u8(v);
+    }
+    uint8_t* q = a.out + (size_t)lane * a.out_lane_stride + (size_t)gy * a.out_step + gx;
+    if (gx + 4 <= a.w0 && ((reinterpret_cast<uintptr_t>(q) & 3) == 0)) {
+        *reinterpret_cast<uint32_t*>(q) = (uint32_t)o8[0] | ((uint32_t)o8[1] << 8) | ((uint32_t)o8[2] << 16) | ((uint32_t)o8[3] << 24);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (gx + i < a.w0) q[i] = o8[i];
+    }
+    if (a.fout) {
+        float* f = a.fout + ((size_t)lane * a.h0 + gy) * a.w0 + gx;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (gx + i < a.w0) f[i] = of[i];
+    }
+}
+
+template <int C>
+__device__ __forceinline__ void egress_pixels(const EgressArgs& a, int lane, int gy, int gx, const float (&up)[C][4]) {
+    const EgressIn<C> in = egress_load<C>(a, lane, gy, gx);
+    egress_convert<C>(a, lane, gy, gx, in, up);
 }
 
 template <int C>
@@ -758,87 +810,6 @@ __global__ void __launch_bounds__(256) k_egress(const EgressArgs a) {
         // when the level-2 window is loaded (entries hold s[upsrc(i)]).
         const bool has2 = a.c2.a != nullptr;
         const int bx2 = x0 / 4 - 2, by2 = y0 / 4 - 2;
-        const float g1 = a.m1.gain;
-        const bool from_state = a.m1.b != nullptr;
-        // Interior tiles (both windows inside their levels: no border rule to apply) build the windows with aligned
-        // 128-bit loads and fixed index arithmetic — a third of the instructions of the generic path below, which
-        // tiles touching an image border keep.  Same operations in the same order, bit-identical values.
-        const bool interior = blockIdx.x >= 1 && blockIdx.y >= 1 && x0 / 2 + 33 <= w1 && y0 / 2 + 17 <= h1 &&
-                              (!has2 || (x0 / 4 + 18 <= a.l2.w && y0 / 4 + 10 <= a.l2.h));
-        if (interior) {
-            if (has2) {
-                // level-2 window rows by2 .. by2+11, columns bx2 .. bx2+19, read as the aligned groups x2 = x0/4-4+4g
-                const bool st2 = a.c2.b != nullptr;
-                for (int i = threadIdx.x; i < C * E2H * 6; i += 256) {
-                    const int ch = i / (E2H * 6), r = i - ch * (E2H * 6);
-                    const int k = r / 6, g = r - k * 6;
-                    const size_t o2 = (size_t)(lane * C + ch) * a.l2.plane + (size_t)(by2 + k) * a.l2.pitch + (x0 / 4 - 4 + 4 * g);
-                    float4 v = __ldg(reinterpret_cast<const float4*>(a.c2.a + o2));
-                    if (st2) {
-                        const float4 u = __ldg(reinterpret_cast<const float4*>(a.c2.b + o2));
-                        v.x = (v.x - u.x) * a.c2.gain; v.y = (v.y - u.y) * a.c2.gain; v.z = (v.z - u.z) * a.c2.gain; v.w = (v.w - u.w) * a.c2.gain;
-                    }
-                    const int j = 4 * g - 2;
-                    float* d = &sC2[ch][k][0];
-                    if (g >= 1) { d[j] = v.x; d[j + 1] = v.y; }
-                    if (g <= 4) { d[j + 2] = v.z; d[j + 3] = v.w; }
-                }
-                __syncthreads();
-                // horizontal pyrUp of each window row at the 34 level-1 columns x0/2-1+j, two columns (odd, even) per item:
-                // x1 = x0/2-1+2p is odd -> (s[i] + s[i+1]) * 4, x1+1 is even -> s[i] + 6 s[i+1] + s[i+2], window index of i = p+1
-                for (int i = threadIdx.x; i < C * E2H * 17; i += 256) {
-                    const int ch = i / (E2H * 17), r = i - ch * (E2H * 17);
-                    const int ky = r / 17, p = r - ky * 17;
-                    const float s0 = sC2[ch][ky][p + 1], s1 = sC2[ch][ky][p + 2], s2 = sC2[ch][ky][p + 3];
-                    float2 o;
-                    o.x = (s0 + s1) * 4.0f;
-                    o.y = s0 + s1 * 6.0f + s2;
-                    *reinterpret_cast<float2*>(&sT[ch][ky][2 * p]) = o;
-                }
-                __syncthreads();
-            }
-            // level-1 window rows y0/2-1+k: columns j = 1 .. 32 as eight aligned groups of four (x1 = x0/2+4g), then the
-            // two edge columns j = 0 and j = 33 one value at a time
-            for (int i = threadIdx.x; i < C * DH * 8 + C * DH * 2; i += 256) {
-                const bool grp = i < C * DH * 8;
-                const int ii = grp ? i : i - C * DH * 8;
-                const int per = grp ? DH * 8 : DH * 2;
-                const int ch = ii / per, r = ii - ch * per;
-                const int k = grp ? r >> 3 : r >> 1, g = grp ? r & 7 : r & 1;
-                const int j0 = grp ? 4 * g + 1 : 33 * g;
-                const size_t o1 = (size_t)(lane * C + ch) * a.l1.plane + (size_t)(y0 / 2 - 1 + k) * a.l1.pitch + (x0 / 2 - 1 + j0);
-                const int ky = ((k - 1) >> 1) + 2;        // window row of level-2 pixel y1 >> 1, y1 = y0/2-1+k
-                const bool odd = !(k & 1);                // y1 odd <=> k even (y0/2 is even)
-                if (grp) {
-                    const float4 hv = __ldg(reinterpret_cast<const float4*>(a.m1.a + o1));
-                    float v[4] = {hv.x, hv.y, hv.z, hv.w};
-                    if (from_state) {
-                        const float4 lv4 = __ldg(reinterpret_cast<const float4*>(a.m1.b + o1));
-                        v[0] = (v[0] - lv4.x) * g1; v[1] = (v[1] - lv4.y) * g1; v[2] = (v[2] - lv4.z) * g1; v[3] = (v[3] - lv4.w) * g1;
-                    }
-                    if (has2) {
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const float r0 = sT[ch][ky - 1][j0 + e], r1 = sT[ch][ky][j0 + e], r2 = sT[ch][ky + 1][j0 + e];
-                            const float ue = (r0 + r1 * 6.0f + r2) * kInv64, uo = ((r1 + r2) * 4.0f) * kInv64;
-                            v[e] = (odd ? uo : ue) + v[e];
-                        }
-                    }
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) sD[ch][k][j0 + e] = v[e];
-                } else {
-                    float v = __ldg(a.m1.a + o1);
-                    if (from_state) v = (v - __ldg(a.m1.b + o1)) * g1;
-                    if (has2) {
-                        const float r0 = sT[ch][ky - 1][j0], r1 = sT[ch][ky][j0], r2 = sT[ch][ky + 1][j0];
-                        const float ue = (r0 + r1 * 6.0f + r2) * kInv64, uo = ((r1 + r2) * 4.0f) * kInv64;
-                        v = (odd ? uo : ue) + v;
-                    }
-                    sD[ch][k][j0] = v;
-                }
-            }
-            __syncthreads();
-        } else {
         if (has2) {
             {
                 const size_t base2 = (size_t)(lane * C) * a.l2.plane;
@@ -859,7 +830,7 @@ __global__ void __launch_bounds__(256) k_egress(const EgressArgs a) {
 #pragma unroll
                 for (int ch = 0; ch < C; ++ch) {
                     const float sm = sC2[ch][r][cm], s0 = sC2[ch][r][c0], sp = sC2[ch][r][cp];
-                    sT[ch][ky][j] = odd ? (s0 + sp) * 4.0f : (sm + s0 * 6.0f + sp);
+                    sT[ch][ky][j] = odd ? up2(s0, sp) : up3(sm, s0, sp);
                 }
             }
             __syncthreads();
@@ -871,6 +842,8 @@ __global__ void __launch_bounds__(256) k_egress(const EgressArgs a) {
             ph[ch] = a.m1.a + (size_t)(lane * C + ch) * a.l1.plane;
             pl[ch] = a.m1.b ? a.m1.b + (size_t)(lane * C + ch) * a.l1.plane : nullptr;
         }
+        const float g1 = a.m1.gain;
+        const bool from_state = a.m1.b != nullptr;
         for (int i = threadIdx.x; i < DH * DW; i += 256) {
             const int k = i / DW, j = i - k * DW;
             const int y1 = upsrc(y0 / 2 - 1 + k, h1), x1 = upsrc(x0 / 2 - 1 + j, w1);
@@ -879,7 +852,7 @@ __global__ void __launch_bounds__(256) k_egress(const EgressArgs a) {
 #pragma unroll
             for (int ch = 0; ch < C; ++ch) {
                 v[ch] = __ldg(ph[ch] + o1);
-                if (from_state) v[ch] = (v[ch] - __ldg(pl[ch] + o1)) * g1;
+                if (from_state) v[ch] = band_of(v[ch], __ldg(pl[ch] + o1), g1);
             }
             if (has2) {
                 const int ky = (y1 >> 1) - by2;
@@ -887,15 +860,13 @@ __global__ void __launch_bounds__(256) k_egress(const EgressArgs a) {
 #pragma unroll
                 for (int ch = 0; ch < C; ++ch) {
                     const float r0 = sT[ch][ky - 1][j], r1 = sT[ch][ky][j], r2 = sT[ch][ky + 1][j];
-                    const float up = odd ? ((r1 + r2) * 4.0f) * kInv64 : (r0 + r1 * 6.0f + r2) * kInv64;
-                    v[ch] = up + v[ch];
+                    v[ch] = __fmaf_rn(odd ? up2(r1, r2) : up3(r0, r1, r2), kInv64, v[ch]);
                 }
             }
 #pragma unroll
             for (int ch = 0; ch < C; ++ch) sD[ch][k][j] = v[ch];
         }
         __syncthreads();
-        }
     }
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const int gx = x0 + 4 * tx;
@@ -909,15 +880,15 @@ __global__ void __launch_bounds__(256) k_egress(const EgressArgs a) {
             for (int q = 0; q < 3; ++q) {
                 const float2 p0 = *reinterpret_cast<const float2*>(&sD[ch][ty + q][2 * tx]);
                 const float2 p1 = *reinterpret_cast<const float2*>(&sD[ch][ty + q][2 * tx + 2]);
-                e[q][0] = p0.x + p0.y * 6.0f + p1.x;
-                e[q][1] = (p0.y + p1.x) * 4.0f;
-                e[q][2] = p0.y + p1.x * 6.0f + p1.y;
-                e[q][3] = (p1.x + p1.y) * 4.0f;
+                e[q][0] = up3(p0.x, p0.y, p1.x);
+                e[q][1] = up2(p0.y, p1.x);
+                e[q][2] = up3(p0.y, p1.x, p1.y);
+                e[q][3] = up2(p1.x, p1.y);
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                up[ch][0][i] = (e[0][i] + e[1][i] * 6.0f + e[2][i]) * kInv64;
-                up[ch][1][i] = ((e[1][i] + e[2][i]) * 4.0f) * kInv64;
+                up[ch][0][i] = __fmul_rn(up3(e[0][i], e[1][i], e[2][i]), kInv64);
+                up[ch][1][i] = __fmul_rn(up2(e[1][i], e[2][i]), kInv64);
             }
         }
     }
@@ -946,6 +917,9 @@ __global__ void __launch_bounds__(256) k_egress(const EgressArgs a) {
 // ------------------------------------------------------------------------------------------------
 constexpr int EG_ROWS = 64;   // output rows per warp (a multiple of 4)
 
+template <int C> struct StripM1 { float2 h[C], l[C]; };   // band-1 source of one cur_1 row at the lane's two columns
+template <int C> struct StripH2 { float v[C], vr[C]; };   // one level-2 row at the lane's column (+ lane 31's right neighbour)
+
 template <int C>
 __global__ void __launch_bounds__(32) k_egress_strip(const EgressArgs a) {
     const unsigned full = 0xffffffffu;
@@ -968,12 +942,13 @@ __global__ void __launch_bounds__(32) k_egress_strip(const EgressArgs a) {
     }
     const int w1 = a.l1.w, h1 = a.l1.h, w2 = a.l2.w, h2 = a.l2.h;
     const int x1a = gx >> 1, x2 = gx >> 2;                           // lane 0 of strip 0: -2, -1
-    const bool has2 = a.c2.a != nullptr, from_state = a.m1.b != nullptr;
-    const float g1 = a.m1.gain;
+    const bool has2 = a.c2.a != nullptr, from_state = a.m1.b != nullptr, st2 = a.c2.b != nullptr;
+    const float g1 = a.m1.gain, g2 = a.c2.gain;
     // clamped columns for the loads of lanes outside the level (their values are never used)
     const int x1l = x1a < 0 ? 0 : (x1a >= w1 ? ((w1 - 1) & ~1) : x1a);
     const int x2l = x2 < 0 ? 0 : (x2 >= w2 ? w2 - 1 : x2);
     const int x2r = x2l + 1 >= w2 ? w2 - 1 : x2l + 1;                // lane 31's right neighbour column
+    const int gxl = px_owner ? gx : 0;                               // input column for the (unused) loads of non-owners
     size_t base1[C], base2[C];
 #pragma unroll
     for (int ch = 0; ch < C; ++ch) {
@@ -981,90 +956,122 @@ __global__ void __launch_bounds__(32) k_egress_strip(const EgressArgs a) {
         base2[ch] = (size_t)(lane * C + ch) * a.l2.plane;
     }
 
-    // H2 window: horizontally expanded level-2 rows (i-1, i, i+1) at the lane's two level-1 columns (even, odd)
-    float hA[C][2], hB[C][2], hC[C][2];
+    // ---- loads (issued one iteration ahead of their use) ----
+    auto ld_m1 = [&](int y1) {                     // y1 is clamped into the level: rows past the end are border copies
+        StripM1<C> m;
+        const size_t ro = (size_t)(y1 < h1 ? y1 : h1 - 1) * a.l1.pitch;
 #pragma unroll
-    for (int ch = 0; ch < C; ++ch) hA[ch][0] = hA[ch][1] = hB[ch][0] = hB[ch][1] = hC[ch][0] = hC[ch][1] = 0.0f;
-    auto load_h2 = [&](int y2, float (&h)[C][2]) {
+        for (int ch = 0; ch < C; ++ch) {
+            m.h[ch] = __ldg(reinterpret_cast<const float2*>(a.m1.a + base1[ch] + ro));
+            m.l[ch] = from_state ? __ldg(reinterpret_cast<const float2*>(a.m1.b + base1[ch] + ro)) : make_float2(0.f, 0.f);
+        }
+        return m;
+    };
+    auto ld_h2 = [&](int y2) {
+        StripH2<C> r;
         const size_t ro = (size_t)upsrc(y2, h2) * a.l2.pitch;
 #pragma unroll
         for (int ch = 0; ch < C; ++ch) {
-            const float v = band_at(a.c2, base2[ch] + ro + x2l);
-            float l = __shfl_up_sync(full, v, 1), r = __shfl_down_sync(full, v, 1);
-            if (lane_id == 31) r = band_at(a.c2, base2[ch] + ro + x2r);
-            if (x2 == 0) l = r;                    // s[-1] := s[1]
-            if (x2 + 1 >= w2) r = v;               // s[w2] := s[w2-1]
-            h[ch][0] = l + v * 6.0f + r;
-            h[ch][1] = (v + r) * 4.0f;
+            float v = 0.f, vr = 0.f;
+            if (has2) {
+                v = __ldg(a.c2.a + base2[ch] + ro + x2l);
+                if (st2) v = band_of(v, __ldg(a.c2.b + base2[ch] + ro + x2l), g2);
+                if (lane_id == 31) {
+                    vr = __ldg(a.c2.a + base2[ch] + ro + x2r);
+                    if (st2) vr = band_of(vr, __ldg(a.c2.b + base2[ch] + ro + x2r), g2);
+                }
+            }
+            r.v[ch] = v; r.vr[ch] = vr;
         }
+        return r;
     };
-    // cur_1 row y1 (inside the level) at the lane's two columns = pyrUp(cur_2) + m_1, then its horizontal expansion
-    // at the lane's four output columns.  `odd`: y1 odd -> level-2 rows (p, q) only.
-    auto cur1_row = [&](int y1, bool odd, const float (&p)[C][2], const float (&q)[C][2], const float (&r)[C][2], float (&E)[C][4]) {
-        const size_t ro = (size_t)y1 * a.l1.pitch;
+    // ---- compute ----
+    // H2 window: horizontally expanded level-2 rows (i-1, i, i+1) at the lane's two level-1 columns (even, odd)
+    float hA[C][2], hB[C][2], hC[C][2];
+    auto expand_h2 = [&](const StripH2<C>& in, float (&h)[C][2]) {
 #pragma unroll
         for (int ch = 0; ch < C; ++ch) {
-            const float2 hv = __ldg(reinterpret_cast<const float2*>(a.m1.a + base1[ch] + ro));
-            float ca = hv.x, cb = hv.y;
+            const float v = in.v[ch];
+            float l = __shfl_up_sync(full, v, 1), r = __shfl_down_sync(full, v, 1);
+            if (lane_id == 31) r = in.vr[ch];
+            if (x2 == 0) l = r;                    // s[-1] := s[1]
+            if (x2 + 1 >= w2) r = v;               // s[w2] := s[w2-1]
+            h[ch][0] = up3(l, v, r);
+            h[ch][1] = up2(v, r);
+        }
+    };
+    // cur_1 row at the lane's two columns = pyrUp(cur_2) + m_1, then its horizontal expansion at the lane's four
+    // output columns.  `odd`: an odd row takes level-2 rows (p, q) only.
+    auto cur1_row = [&](const StripM1<C>& m, bool odd, const float (&p)[C][2], const float (&q)[C][2], const float (&r)[C][2], float (&E)[C][4]) {
+#pragma unroll
+        for (int ch = 0; ch < C; ++ch) {
+            float ca = m.h[ch].x, cb = m.h[ch].y;
             if (from_state) {
-                const float2 lv2 = __ldg(reinterpret_cast<const float2*>(a.m1.b + base1[ch] + ro));
-                ca = (ca - lv2.x) * g1;
-                cb = (cb - lv2.y) * g1;
+                ca = band_of(ca, m.l[ch].x, g1);
+                cb = band_of(cb, m.l[ch].y, g1);
             }
             if (has2) {
-                const float ua = odd ? ((p[ch][0] + q[ch][0]) * 4.0f) * kInv64 : (p[ch][0] + q[ch][0] * 6.0f + r[ch][0]) * kInv64;
-                const float ub = odd ? ((p[ch][1] + q[ch][1]) * 4.0f) * kInv64 : (p[ch][1] + q[ch][1] * 6.0f + r[ch][1]) * kInv64;
-                ca = ua + ca;
-                cb = ub + cb;
+                ca = __fmaf_rn(odd ? up2(p[ch][0], q[ch][0]) : up3(p[ch][0], q[ch][0], r[ch][0]), kInv64, ca);
+                cb = __fmaf_rn(odd ? up2(p[ch][1], q[ch][1]) : up3(p[ch][1], q[ch][1], r[ch][1]), kInv64, cb);
             }
             if (x1a + 1 >= w1) cb = ca;                                  // cur_1[w1] := cur_1[w1-1]
             float left = __shfl_up_sync(full, cb, 1), right = __shfl_down_sync(full, ca, 1);
             if (x1a == 0) left = cb;                                     // cur_1[-1] := cur_1[1]
             if (x1a + 2 >= w1) right = cb;
-            E[ch][0] = left + ca * 6.0f + cb;
-            E[ch][1] = (ca + cb) * 4.0f;
-            E[ch][2] = ca + cb * 6.0f + right;
-            E[ch][3] = (cb + right) * 4.0f;
+            E[ch][0] = up3(left, ca, cb);
+            E[ch][1] = up2(ca, cb);
+            E[ch][2] = up3(ca, cb, right);
+            E[ch][3] = up2(cb, right);
         }
     };
 
     const int j0 = f0 >> 1;                       // first level-1 row of the chunk (even)
     float Em[C][4], E0[C][4], Ep[C][4];
-    if (has2) {
+    StripH2<C> nh;
+    {
         const int ic = j0 >> 1;
-        load_h2(ic - 1, hA);
-        load_h2(ic, hB);
-        load_h2(ic + 1, hC);
+        const StripH2<C> ra = ld_h2(ic - 1), rb = ld_h2(ic), rc = ld_h2(ic + 1);
+        const StripM1<C> mp = ld_m1(j0 > 0 ? j0 - 1 : 0), m0 = ld_m1(j0);
+        expand_h2(ra, hA);
+        expand_h2(rb, hB);
+        expand_h2(rc, hC);
+        cur1_row(mp, true, hA, hB, hC, Em);       // odd row j0-1 of the previous window centre: level-2 rows (ic-1, ic);
+        cur1_row(m0, false, hA, hB, hC, E0);      // (at the top of the image Em is replaced by row 1 below)
+        nh = rc;                                  // placeholder: the first iteration (odd row) requests the next level-2 row itself
     }
-    if (j0 > 0) cur1_row(j0 - 1, true, hA, hB, hC, Em);      // odd row of the previous window centre: level-2 rows (ic-1, ic)
-    else {
-#pragma unroll
-        for (int ch = 0; ch < C; ++ch)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) Em[ch][i] = 0.0f;    // replaced by row 1 below
-    }
-    cur1_row(j0, false, hA, hB, hC, E0);
     const int j_end = (f_end + 1) >> 1;
+    // requests for the first iteration
+    StripM1<C> nm = ld_m1(j0 + 1);
+    EgressIn<C> nin0 = egress_load<C>(a, lane, 2 * j0, gxl);
+    EgressIn<C> nin1 = egress_load<C>(a, lane, min(2 * j0 + 1, a.h0 - 1), gxl);
     for (int j = j0; j < j_end; ++j) {
-        // row j+1 of cur_1 (or its border copy) -> Ep
         const int jn = j + 1;
+        const StripM1<C> cm = nm;
+        const StripH2<C> chh = nh;
+        const EgressIn<C> in0 = nin0, in1 = nin1;
+        // requests for the next iteration: cur_1 row j+2, the level-2 row that enters the window with it, the inputs
+        if (jn < j_end) {
+            nm = ld_m1(jn + 1);
+            if (jn & 1) nh = ld_h2(((jn + 1) >> 1) + 1);
+            nin0 = egress_load<C>(a, lane, min(2 * jn, a.h0 - 1), gxl);
+            nin1 = egress_load<C>(a, lane, min(2 * jn + 1, a.h0 - 1), gxl);
+        }
+        // row j+1 of cur_1 (or its border copy) -> Ep
         if (jn >= h1) {
 #pragma unroll
             for (int ch = 0; ch < C; ++ch)
 #pragma unroll
                 for (int i = 0; i < 4; ++i) Ep[ch][i] = E0[ch][i];
         } else if (jn & 1) {
-            cur1_row(jn, true, hB, hC, hC, Ep);              // odd: level-2 rows (i, i+1) of the current centre
+            cur1_row(cm, true, hB, hC, hC, Ep);              // odd: level-2 rows (i, i+1) of the current centre
         } else {
-            if (has2) {                                      // slide the level-2 window to centre jn / 2
 #pragma unroll
-                for (int ch = 0; ch < C; ++ch) {
-                    hA[ch][0] = hB[ch][0]; hA[ch][1] = hB[ch][1];
-                    hB[ch][0] = hC[ch][0]; hB[ch][1] = hC[ch][1];
-                }
-                load_h2((jn >> 1) + 1, hC);
+            for (int ch = 0; ch < C; ++ch) {                 // slide the level-2 window to centre jn / 2
+                hA[ch][0] = hB[ch][0]; hA[ch][1] = hB[ch][1];
+                hB[ch][0] = hC[ch][0]; hB[ch][1] = hC[ch][1];
             }
-            cur1_row(jn, false, hA, hB, hC, Ep);
+            expand_h2(chh, hC);
+            cur1_row(cm, false, hA, hB, hC, Ep);
         }
         if (j == 0) {
 #pragma unroll
@@ -1077,14 +1084,14 @@ __global__ void __launch_bounds__(32) k_egress_strip(const EgressArgs a) {
 #pragma unroll
             for (int ch = 0; ch < C; ++ch)
 #pragma unroll
-                for (int i = 0; i < 4; ++i) up[ch][i] = (Em[ch][i] + E0[ch][i] * 6.0f + Ep[ch][i]) * kInv64;
-            egress_pixels<C>(a, lane, 2 * j, gx, up);
+                for (int i = 0; i < 4; ++i) up[ch][i] = __fmul_rn(up3(Em[ch][i], E0[ch][i], Ep[ch][i]), kInv64);
+            egress_convert<C>(a, lane, 2 * j, gx, in0, up);
             if (2 * j + 1 < f_end) {
 #pragma unroll
                 for (int ch = 0; ch < C; ++ch)
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) up[ch][i] = ((E0[ch][i] + Ep[ch][i]) * 4.0f) * kInv64;
-                egress_pixels<C>(a, lane, 2 * j + 1, gx, up);
+                    for (int i = 0; i < 4; ++i) up[ch][i] = __fmul_rn(up2(E0[ch][i], Ep[ch][i]), kInv64);
+                egress_convert<C>(a, lane, 2 * j + 1, gx, in1, up);
             }
         }
 #pragma unroll
