@@ -110,7 +110,7 @@ cudaError_t launch_collapse(const Level& lf, const Level& lc, const BandSrc& fin
 // m1.a == nullptr: no motion; c2.a == nullptr: cur_1 = m1.  C == 3 reads `lab`, C == 1 reads io.in.
 cudaError_t launch_egress(const FrameIO& io, const DeviceTables& tb, const int16_t* lab, int pitch16, size_t plane16,
                           const BandSrc& m1, const Level& l1, const BandSrc& c2, const Level& l2, float chroma,
-                          float* float_out_or_null, cudaStream_t s, bool strip = true);
+                          float* float_out_or_null, cudaStream_t s, int strip = 20);
 
 // PreprocessProcessor + GrayscaleProcessor on the device (mc_preprocess.cu)
 cudaError_t launch_preprocess(const uint8_t* src_roi, size_t step, int cn, int sw, int sh, int dw, int dh, bool copy_only,

@@ -920,8 +920,8 @@ constexpr int EG_ROWS = 64;   // output rows per warp (a multiple of 4)
 template <int C> struct StripM1 { float2 h[C], l[C]; };   // band-1 source of one cur_1 row at the lane's two columns
 template <int C> struct StripH2 { float v[C], vr[C]; };   // one level-2 row at the lane's column (+ lane 31's right neighbour)
 
-template <int C>
-__global__ void __launch_bounds__(32) k_egress_strip(const EgressArgs a) {
+template <int C, int MINB>
+__global__ void __launch_bounds__(32, MINB) k_egress_strip(const EgressArgs a) {
     const unsigned full = 0xffffffffu;
     const int lane_id = threadIdx.x;
     const int lane = blockIdx.z;
@@ -986,9 +986,16 @@ __global__ void __launch_bounds__(32) k_egress_strip(const EgressArgs a) {
         return r;
     };
     // ---- compute ----
-    // H2 window: horizontally expanded level-2 rows (i-1, i, i+1) at the lane's two level-1 columns (even, odd)
-    float hA[C][2], hB[C][2], hC[C][2];
-    auto expand_h2 = [&](const StripH2<C>& in, float (&h)[C][2]) {
+    // The two sliding windows live in shared memory as per-lane rings of three rows (each lane only ever reads back what
+    // it stored itself, so no synchronisation is involved): they would otherwise hold 54 registers across the whole
+    // pixel stage and halve the number of resident warps of an issue-bound kernel.
+    //   sH[i % 3]: horizontally expanded level-2 row i at the lane's two level-1 columns (even, odd)
+    //   sE[j % 3]: horizontally expanded cur_1 row j at the lane's four output columns
+    __shared__ float2 sH[3][C][32];
+    __shared__ float4 sE[3][C][32];
+    auto slot = [](int r) { return (r + 3) % 3; };      // rows >= -1
+    auto expand_h2 = [&](const StripH2<C>& in, int i) {
+        const int sl = slot(i);
 #pragma unroll
         for (int ch = 0; ch < C; ++ch) {
             const float v = in.v[ch];
@@ -996,13 +1003,15 @@ __global__ void __launch_bounds__(32) k_egress_strip(const EgressArgs a) {
             if (lane_id == 31) r = in.vr[ch];
             if (x2 == 0) l = r;                    // s[-1] := s[1]
             if (x2 + 1 >= w2) r = v;               // s[w2] := s[w2-1]
-            h[ch][0] = up3(l, v, r);
-            h[ch][1] = up2(v, r);
+            sH[sl][ch][lane_id] = make_float2(up3(l, v, r), up2(v, r));
         }
     };
-    // cur_1 row at the lane's two columns = pyrUp(cur_2) + m_1, then its horizontal expansion at the lane's four
-    // output columns.  `odd`: an odd row takes level-2 rows (p, q) only.
-    auto cur1_row = [&](const StripM1<C>& m, bool odd, const float (&p)[C][2], const float (&q)[C][2], const float (&r)[C][2], float (&E)[C][4]) {
+    // cur_1 row y1 at the lane's two columns = pyrUp(cur_2) + m_1, then its horizontal expansion at the lane's four
+    // output columns.  An even row 2i takes level-2 rows (i-1, i, i+1), an odd row 2i+1 rows (i, i+1).
+    auto cur1_row = [&](const StripM1<C>& m, int y1, float (&E)[C][4]) {
+        const bool odd = y1 & 1;
+        const int i = y1 >> 1;
+        const int sp = slot(odd ? i : i - 1), sq = slot(odd ? i + 1 : i), sr = slot(i + 1);
 #pragma unroll
         for (int ch = 0; ch < C; ++ch) {
             float ca = m.h[ch].x, cb = m.h[ch].y;
@@ -1011,8 +1020,9 @@ __global__ void __launch_bounds__(32) k_egress_strip(const EgressArgs a) {
                 cb = band_of(cb, m.l[ch].y, g1);
             }
             if (has2) {
-                ca = __fmaf_rn(odd ? up2(p[ch][0], q[ch][0]) : up3(p[ch][0], q[ch][0], r[ch][0]), kInv64, ca);
-                cb = __fmaf_rn(odd ? up2(p[ch][1], q[ch][1]) : up3(p[ch][1], q[ch][1], r[ch][1]), kInv64, cb);
+                const float2 p = sH[sp][ch][lane_id], q = sH[sq][ch][lane_id], r = sH[sr][ch][lane_id];
+                ca = __fmaf_rn(odd ? up2(p.x, q.x) : up3(p.x, q.x, r.x), kInv64, ca);
+                cb = __fmaf_rn(odd ? up2(p.y, q.y) : up3(p.y, q.y, r.y), kInv64, cb);
             }
             if (x1a + 1 >= w1) cb = ca;                                  // cur_1[w1] := cur_1[w1-1]
             float left = __shfl_up_sync(full, cb, 1), right = __shfl_down_sync(full, ca, 1);
@@ -1024,19 +1034,26 @@ __global__ void __launch_bounds__(32) k_egress_strip(const EgressArgs a) {
             E[ch][3] = up2(cb, right);
         }
     };
+    auto put_E = [&](int j, const float (&E)[C][4]) {
+        const int sl = slot(j);
+#pragma unroll
+        for (int ch = 0; ch < C; ++ch) sE[sl][ch][lane_id] = make_float4(E[ch][0], E[ch][1], E[ch][2], E[ch][3]);
+    };
 
     const int j0 = f0 >> 1;                       // first level-1 row of the chunk (even)
-    float Em[C][4], E0[C][4], Ep[C][4];
     StripH2<C> nh;
     {
         const int ic = j0 >> 1;
         const StripH2<C> ra = ld_h2(ic - 1), rb = ld_h2(ic), rc = ld_h2(ic + 1);
-        const StripM1<C> mp = ld_m1(j0 > 0 ? j0 - 1 : 0), m0 = ld_m1(j0);
-        expand_h2(ra, hA);
-        expand_h2(rb, hB);
-        expand_h2(rc, hC);
-        cur1_row(mp, true, hA, hB, hC, Em);       // odd row j0-1 of the previous window centre: level-2 rows (ic-1, ic);
-        cur1_row(m0, false, hA, hB, hC, E0);      // (at the top of the image Em is replaced by row 1 below)
+        const StripM1<C> mp = ld_m1(j0 > 0 ? j0 - 1 : 1), m0 = ld_m1(j0);
+        expand_h2(ra, ic - 1);
+        expand_h2(rb, ic);
+        expand_h2(rc, ic + 1);
+        float E[C][4];
+        // row j0-1 (odd, level-2 rows ic-1, ic); at the top of the image the slot of row -1 is filled with row 1 below
+        if (j0 > 0) { cur1_row(mp, j0 - 1, E); put_E(j0 - 1, E); }
+        cur1_row(m0, j0, E);
+        put_E(j0, E);
         nh = rc;                                  // placeholder: the first iteration (odd row) requests the next level-2 row itself
     }
     const int j_end = (f_end + 1) >> 1;
@@ -1057,47 +1074,41 @@ __global__ void __launch_bounds__(32) k_egress_strip(const EgressArgs a) {
             nin1 = egress_load<C>(a, lane, min(2 * jn + 1, a.h0 - 1), gxl);
         }
         // row j+1 of cur_1 (or its border copy) -> Ep
+        float Ep[C][4];
         if (jn >= h1) {
+            const int s0 = slot(j);
 #pragma unroll
-            for (int ch = 0; ch < C; ++ch)
-#pragma unroll
-                for (int i = 0; i < 4; ++i) Ep[ch][i] = E0[ch][i];
-        } else if (jn & 1) {
-            cur1_row(cm, true, hB, hC, hC, Ep);              // odd: level-2 rows (i, i+1) of the current centre
-        } else {
-#pragma unroll
-            for (int ch = 0; ch < C; ++ch) {                 // slide the level-2 window to centre jn / 2
-                hA[ch][0] = hB[ch][0]; hA[ch][1] = hB[ch][1];
-                hB[ch][0] = hC[ch][0]; hB[ch][1] = hC[ch][1];
+            for (int ch = 0; ch < C; ++ch) {
+                const float4 e = sE[s0][ch][lane_id];
+                Ep[ch][0] = e.x; Ep[ch][1] = e.y; Ep[ch][2] = e.z; Ep[ch][3] = e.w;
             }
-            expand_h2(chh, hC);
-            cur1_row(cm, false, hA, hB, hC, Ep);
+        } else {
+            if (!(jn & 1)) expand_h2(chh, (jn >> 1) + 1);     // an even row moves the level-2 window to centre jn / 2
+            cur1_row(cm, jn, Ep);
         }
-        if (j == 0) {
-#pragma unroll
-            for (int ch = 0; ch < C; ++ch)
-#pragma unroll
-                for (int i = 0; i < 4; ++i) Em[ch][i] = Ep[ch][i];       // cur_1[-1] := cur_1[1]
-        }
+        put_E(jn, Ep);
+        if (j == 0) put_E(-1, Ep);                            // cur_1[-1] := cur_1[1]
         if (px_owner) {
-            float up[C][4];
+            const int sm = slot(j - 1), s0 = slot(j);
+            float up[C][4], t0[C][4];
 #pragma unroll
-            for (int ch = 0; ch < C; ++ch)
-#pragma unroll
-                for (int i = 0; i < 4; ++i) up[ch][i] = __fmul_rn(up3(Em[ch][i], E0[ch][i], Ep[ch][i]), kInv64);
+            for (int ch = 0; ch < C; ++ch) {
+                const float4 em = sE[sm][ch][lane_id], e0 = sE[s0][ch][lane_id];
+                t0[ch][0] = e0.x; t0[ch][1] = e0.y; t0[ch][2] = e0.z; t0[ch][3] = e0.w;
+                up[ch][0] = __fmul_rn(up3(em.x, e0.x, Ep[ch][0]), kInv64);
+                up[ch][1] = __fmul_rn(up3(em.y, e0.y, Ep[ch][1]), kInv64);
+                up[ch][2] = __fmul_rn(up3(em.z, e0.z, Ep[ch][2]), kInv64);
+                up[ch][3] = __fmul_rn(up3(em.w, e0.w, Ep[ch][3]), kInv64);
+            }
             egress_convert<C>(a, lane, 2 * j, gx, in0, up);
             if (2 * j + 1 < f_end) {
 #pragma unroll
                 for (int ch = 0; ch < C; ++ch)
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) up[ch][i] = __fmul_rn(up2(E0[ch][i], Ep[ch][i]), kInv64);
+                    for (int i = 0; i < 4; ++i) up[ch][i] = __fmul_rn(up2(t0[ch][i], Ep[ch][i]), kInv64);
                 egress_convert<C>(a, lane, 2 * j + 1, gx, in1, up);
             }
         }
-#pragma unroll
-        for (int ch = 0; ch < C; ++ch)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) { Em[ch][i] = E0[ch][i]; E0[ch][i] = Ep[ch][i]; }
     }
 }
 
@@ -1210,7 +1221,7 @@ cudaError_t launch_collapse(const Level& lf, const Level& lc, const BandSrc& fin
 
 cudaError_t launch_egress(const FrameIO& io, const DeviceTables& tb, const int16_t* lab, int pitch16, size_t plane16,
                           const BandSrc& m1, const Level& l1, const BandSrc& c2, const Level& l2, float chroma,
-                          float* fout, cudaStream_t s, bool strip) {
+                          float* fout, cudaStream_t s, int strip) {
     EgressArgs a;
     a.in = io.in; a.in_step = io.in_step; a.in_lane_stride = io.in_lane_stride;
     a.lab = lab; a.pitch16 = pitch16; a.plane16 = plane16;
@@ -1220,8 +1231,11 @@ cudaError_t launch_egress(const FrameIO& io, const DeviceTables& tb, const int16
     a.m1 = m1; a.l1 = l1; a.c2 = c2; a.l2 = l2; a.chroma = chroma; a.fout = fout;
     if (strip) {
         dim3 grid(cdiv(io.w, DS_COLS), cdiv(io.h, EG_ROWS), io.lanes);
-        if (io.channels == 3) k_egress_strip<3><<<grid, 32, 0, s>>>(a);
-        else k_egress_strip<1><<<grid, 32, 0, s>>>(a);
+        // the register cap (resident warps per SM) is an A/B knob: 16 -> <= 128 registers, 20 -> 96, 24 -> 80
+        if (io.channels != 3) k_egress_strip<1, 24><<<grid, 32, 0, s>>>(a);
+        else if (strip == 16) k_egress_strip<3, 16><<<grid, 32, 0, s>>>(a);
+        else if (strip == 24) k_egress_strip<3, 24><<<grid, 32, 0, s>>>(a);
+        else k_egress_strip<3, 20><<<grid, 32, 0, s>>>(a);
     } else {
         dim3 grid(cdiv(io.w, TW), cdiv(io.h, TH), io.lanes);
         if (io.channels == 3) k_egress<3><<<grid, 256, 0, s>>>(a);

@@ -38,7 +38,8 @@ struct ModeCtx {
     bool use_tma;      // stage level-kernel tiles with cp.async.bulk.tensor (option "use_tma", default on)
     bool prefetch_state;    // level kernel requests its state tiles by TMA at kernel entry (option "prefetch_state", default on:
                             // B200, 32 lanes: level[1] 235 -> 205 us)
-    bool egress_strip;      // Laplace egress as the register/shuffle strip kernel (option "egress_strip", default on; 0: tile kernel)
+    int egress_strip;       // Laplace egress as the register/shuffle strip kernel (option "egress_strip": 0 = tile kernel,
+                            // 16 / 20 / 24 = strip kernel compiled for that many resident warps per SM)
     int ingest_warps;       // warps per CTA of the fused ingest kernel (option "ingest_warps": 1, 2 or 4)
     bool band_from_state;   // synthesis rebuilds gain*(hi-lo) from the state planes instead of reading a stored band
                             // (option "band_from_state", default on: with prefetch_state level[1] 205 -> 177 us, egress +8 us)
