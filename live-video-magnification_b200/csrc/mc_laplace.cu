@@ -59,6 +59,15 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, in
 
 #endif
 
+// request a line into L1 ahead of its use (no register is tied up, unlike a load issued early)
+__device__ __forceinline__ void prefetch_l1(const void* p) {
+#if !defined(MC_CUDA_EMU)
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
+
 constexpr float kInv256 = 1.0f / 256.0f;
 constexpr float kInv64 = 1.0f / 64.0f;
 
@@ -918,7 +927,7 @@ __global__ void __launch_bounds__(256) k_egress(const EgressArgs a) {
 constexpr int EG_ROWS = 64;   // output rows per warp (a multiple of 4)
 
 template <int C> struct StripM1 { float2 h[C], l[C]; };   // band-1 source of one cur_1 row at the lane's two columns
-template <int C> struct StripH2 { float v[C], vr[C]; };   // one level-2 row at the lane's column (+ lane 31's right neighbour)
+template <int C> struct StripH2 { float v[C], vb[C], vr[C], vrb[C]; };   // one level-2 row at the lane's column (+ lane 31's right neighbour); b: lo state
 
 template <int C, int MINB>
 __global__ void __launch_bounds__(32, MINB) k_egress_strip(const EgressArgs a) {
@@ -956,10 +965,11 @@ __global__ void __launch_bounds__(32, MINB) k_egress_strip(const EgressArgs a) {
         base2[ch] = (size_t)(lane * C + ch) * a.l2.plane;
     }
 
-    // ---- loads (issued one iteration ahead of their use) ----
-    auto ld_m1 = [&](int y1) {                     // y1 is clamped into the level: rows past the end are border copies
+    // ---- loads; the lines of the next iteration are requested into L1 while the current one is computed ----
+    auto row1 = [&](int y1) { return (size_t)(y1 < h1 ? y1 : h1 - 1) * a.l1.pitch; };   // rows past the end are border copies
+    auto ld_m1 = [&](int y1) {
         StripM1<C> m;
-        const size_t ro = (size_t)(y1 < h1 ? y1 : h1 - 1) * a.l1.pitch;
+        const size_t ro = row1(y1);
 #pragma unroll
         for (int ch = 0; ch < C; ++ch) {
             m.h[ch] = __ldg(reinterpret_cast<const float2*>(a.m1.a + base1[ch] + ro));
@@ -967,23 +977,48 @@ __global__ void __launch_bounds__(32, MINB) k_egress_strip(const EgressArgs a) {
         }
         return m;
     };
+    auto pf_m1 = [&](int y1) {
+        const size_t ro = row1(y1);
+#pragma unroll
+        for (int ch = 0; ch < C; ++ch) {
+            prefetch_l1(a.m1.a + base1[ch] + ro);
+            if (from_state) prefetch_l1(a.m1.b + base1[ch] + ro);
+        }
+    };
     auto ld_h2 = [&](int y2) {
         StripH2<C> r;
         const size_t ro = (size_t)upsrc(y2, h2) * a.l2.pitch;
 #pragma unroll
         for (int ch = 0; ch < C; ++ch) {
-            float v = 0.f, vr = 0.f;
+            r.v[ch] = r.vb[ch] = r.vr[ch] = r.vrb[ch] = 0.f;
             if (has2) {
-                v = __ldg(a.c2.a + base2[ch] + ro + x2l);
-                if (st2) v = band_of(v, __ldg(a.c2.b + base2[ch] + ro + x2l), g2);
+                r.v[ch] = __ldg(a.c2.a + base2[ch] + ro + x2l);
+                if (st2) r.vb[ch] = __ldg(a.c2.b + base2[ch] + ro + x2l);
                 if (lane_id == 31) {
-                    vr = __ldg(a.c2.a + base2[ch] + ro + x2r);
-                    if (st2) vr = band_of(vr, __ldg(a.c2.b + base2[ch] + ro + x2r), g2);
+                    r.vr[ch] = __ldg(a.c2.a + base2[ch] + ro + x2r);
+                    if (st2) r.vrb[ch] = __ldg(a.c2.b + base2[ch] + ro + x2r);
                 }
             }
-            r.v[ch] = v; r.vr[ch] = vr;
         }
         return r;
+    };
+    auto pf_h2 = [&](int y2) {
+        const size_t ro = (size_t)upsrc(y2, h2) * a.l2.pitch;
+        if (has2) {
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch) {
+                prefetch_l1(a.c2.a + base2[ch] + ro + x2l);
+                if (st2) prefetch_l1(a.c2.b + base2[ch] + ro + x2l);
+            }
+        }
+    };
+    auto pf_in = [&](int gy) {
+        if (C == 3) {
+            const int16_t* lp = a.lab + (size_t)(lane * 3) * a.plane16 + (size_t)gy * a.pitch16 + gxl;
+            prefetch_l1(lp); prefetch_l1(lp + a.plane16); prefetch_l1(lp + 2 * a.plane16);
+        } else {
+            prefetch_l1(a.in + (size_t)lane * a.in_lane_stride + (size_t)gy * a.in_step + gxl);
+        }
     };
     // ---- compute ----
     // The two sliding windows live in shared memory as per-lane rings of three rows (each lane only ever reads back what
@@ -998,9 +1033,9 @@ __global__ void __launch_bounds__(32, MINB) k_egress_strip(const EgressArgs a) {
         const int sl = slot(i);
 #pragma unroll
         for (int ch = 0; ch < C; ++ch) {
-            const float v = in.v[ch];
+            const float v = st2 ? band_of(in.v[ch], in.vb[ch], g2) : in.v[ch];
             float l = __shfl_up_sync(full, v, 1), r = __shfl_down_sync(full, v, 1);
-            if (lane_id == 31) r = in.vr[ch];
+            if (lane_id == 31) r = st2 ? band_of(in.vr[ch], in.vrb[ch], g2) : in.vr[ch];
             if (x2 == 0) l = r;                    // s[-1] := s[1]
             if (x2 + 1 >= w2) r = v;               // s[w2] := s[w2-1]
             sH[sl][ch][lane_id] = make_float2(up3(l, v, r), up2(v, r));
@@ -1041,11 +1076,13 @@ __global__ void __launch_bounds__(32, MINB) k_egress_strip(const EgressArgs a) {
     };
 
     const int j0 = f0 >> 1;                       // first level-1 row of the chunk (even)
-    StripH2<C> nh;
     {
         const int ic = j0 >> 1;
         const StripH2<C> ra = ld_h2(ic - 1), rb = ld_h2(ic), rc = ld_h2(ic + 1);
         const StripM1<C> mp = ld_m1(j0 > 0 ? j0 - 1 : 1), m0 = ld_m1(j0);
+        pf_m1(j0 + 1);
+        pf_in(2 * j0);
+        pf_in(min(2 * j0 + 1, a.h0 - 1));
         expand_h2(ra, ic - 1);
         expand_h2(rb, ic);
         expand_h2(rc, ic + 1);
@@ -1054,24 +1091,25 @@ __global__ void __launch_bounds__(32, MINB) k_egress_strip(const EgressArgs a) {
         if (j0 > 0) { cur1_row(mp, j0 - 1, E); put_E(j0 - 1, E); }
         cur1_row(m0, j0, E);
         put_E(j0, E);
-        nh = rc;                                  // placeholder: the first iteration (odd row) requests the next level-2 row itself
     }
     const int j_end = (f_end + 1) >> 1;
-    // requests for the first iteration
-    StripM1<C> nm = ld_m1(j0 + 1);
-    EgressIn<C> nin0 = egress_load<C>(a, lane, 2 * j0, gxl);
-    EgressIn<C> nin1 = egress_load<C>(a, lane, min(2 * j0 + 1, a.h0 - 1), gxl);
     for (int j = j0; j < j_end; ++j) {
         const int jn = j + 1;
-        const StripM1<C> cm = nm;
-        const StripH2<C> chh = nh;
-        const EgressIn<C> in0 = nin0, in1 = nin1;
-        // requests for the next iteration: cur_1 row j+2, the level-2 row that enters the window with it, the inputs
+        // what this iteration consumes (requested into L1 by the previous one) ...
+        const StripM1<C> cm = ld_m1(jn);
+        StripH2<C> chh;
+        if (!(jn & 1) && jn < h1) chh = ld_h2((jn >> 1) + 1);
+        EgressIn<C> in0, in1;
+        if (px_owner) {
+            in0 = egress_load<C>(a, lane, 2 * j, gx);
+            in1 = egress_load<C>(a, lane, min(2 * j + 1, a.h0 - 1), gx);
+        }
+        // ... and the requests for the next one: cur_1 row j+2, the level-2 row that enters the window with it, the inputs
         if (jn < j_end) {
-            nm = ld_m1(jn + 1);
-            if (jn & 1) nh = ld_h2(((jn + 1) >> 1) + 1);
-            nin0 = egress_load<C>(a, lane, min(2 * jn, a.h0 - 1), gxl);
-            nin1 = egress_load<C>(a, lane, min(2 * jn + 1, a.h0 - 1), gxl);
+            pf_m1(jn + 1);
+            if (jn & 1) pf_h2(((jn + 1) >> 1) + 1);
+            pf_in(min(2 * jn, a.h0 - 1));
+            pf_in(min(2 * jn + 1, a.h0 - 1));
         }
         // row j+1 of cur_1 (or its border copy) -> Ep
         float Ep[C][4];
