@@ -271,6 +271,9 @@ def run_ours(args, rank, world, local_rank):
     frame_bytes = H * row * lanes
 
     proc = L.MagnificationProcessor(device=local_rank, lanes=lanes)
+    for kv in args.opt:                       # A/B knobs of the library (mc_set_option), e.g. --opt lane_groups=1
+        k, v = kv.split("=")
+        proc.set_option(k, int(v))
     stream = torch.cuda.ExternalStream(proc.stream, device=local_rank)
     clip_d = torch.from_numpy(clip_h).cuda()
     out_d = torch.empty((lanes, H, W, CH), dtype=torch.uint8, device="cuda")
@@ -431,6 +434,7 @@ def main():
     ap.add_argument("--cpu-frames", type=int, default=48)
     ap.add_argument("--ref-frames-per-step", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], help="library option key=value (mc_set_option), repeatable")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))

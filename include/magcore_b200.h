@@ -164,8 +164,13 @@ void* mc_stream(mc_handle* h);
  *   "prefetch_state" (default 1; needs use_tma): the fused level kernel requests the tile's two state planes as TMA
  *        bulk copies at kernel entry, together with its input window, instead of loading them in its last phase
  *        (same results; measured on B200: level[1] 235 -> 205 us per 32-lane launch; 0 kept for A/B measurements)
- *   "egress_strip" (default 1): Laplace egress runs as the register/shuffle strip kernel (one warp per 128-column
- *        strip, no shared memory); 0 selects the shared-memory tile kernel (bit-identical results; kept for A/B)
+ *   "lane_groups" (default 0 = automatic: min(4, lanes / 4), at least 1): Laplace — the lanes of the handle run as
+ *        that many concurrent launch chains on separate CUDA streams, forked from and joined into mc_stream(); the
+ *        L1-bound ingest, issue-bound egress and HBM-bound level kernels of different groups then share the SMs
+ *        instead of running back to back (same results; profile_kernels forces 1)
+ *   "egress_strip" (default 20): Laplace egress runs as the shuffle strip kernel (one warp per 128-column strip,
+ *        sliding windows in per-lane shared-memory rings; the value 16 / 20 / 24 picks the register cap = resident
+ *        warps per SM); 0 selects the shared-memory tile kernel (bit-identical results; kept for A/B)
  *   "ingest_warps" (default 1): warps per CTA (1, 2 or 4) of the fused BGR->Lab ingest kernel (same results; A/B)
  *   "analysis_only" (default 0): Laplace and Phase — frames after the first update the temporal state (EMA planes;
  *        Riesz pyramids, phase accumulators and Butterworth registers) but skip synthesis and egress and report

@@ -43,6 +43,7 @@ struct ModeCtx {
     int ingest_warps;       // warps per CTA of the fused ingest kernel (option "ingest_warps": 1, 2 or 4)
     bool band_from_state;   // synthesis rebuilds gain*(hi-lo) from the state planes instead of reading a stored band
                             // (option "band_from_state", default on: with prefetch_state level[1] 205 -> 177 us, egress +8 us)
+    int lane_groups;        // Laplace: number of lane groups run as concurrent launch chains (option "lane_groups"; 0 = automatic)
     bool analysis_only;     // Laplace / Phase: update the temporal state but skip synthesis + egress (*produced = 0); used by the
                             // state-carry pass of temporal sharding (lvm_b200.shard.magnify_segment)
 };
@@ -55,6 +56,11 @@ struct ModeCtx {
             *ctx.err = std::string(#call) + ": " + cudaGetErrorString(e__);   \
             return MC_ERR_CUDA;                                               \
         }                                                                     \
+    } while (0)
+#define MCK_ST(call)                                                          \
+    do {                                                                      \
+        const mc_status s__ = (call);                                         \
+        if (s__ != MC_OK) return s__;                                         \
     } while (0)
 #define LAUNCH(name, level, call)                                             \
     do {                                                                      \
@@ -97,9 +103,21 @@ struct MotionMode {
     size_t plane16 = 0;
     DeviceArena arena;
 
-    std::vector<TensorMapStorage> tmaps;   // per level: TMA descriptor of G[l] (tmap_valid[l] != 0)
-    std::vector<TensorMapStorage> tmaps_hi, tmaps_lo;   // ... and of the state planes (64 x 32 tiles, option prefetch_state)
-    std::vector<char> tmap_valid;
+    // Lane groups (option "lane_groups"): the streams of a handle are independent, so their launch sets are issued as
+    // `groups.size()` separate chains on separate CUDA streams.  A group's kernels no longer fill the GPU, so the block
+    // scheduler co-schedules different stages of different groups on the same SMs — the L1-bound BGR->Lab ingest of one
+    // group, the issue-bound egress of another and the HBM-bound level kernels of a third — instead of running the
+    // stages back to back.  Buffers stay whole-handle allocations; a group sees them through offset pointers.
+    struct Group {
+        int lane0 = 0, lanes = 0;
+        cudaStream_t stream = nullptr;     // null: the handle's stream (single group)
+        cudaEvent_t done = nullptr;
+        std::vector<TensorMapStorage> tmaps, tmaps_hi, tmaps_lo;   // per level: TMA descriptors of G[l] / hi[l] / lo[l] of this group's planes
+        std::vector<char> tmap_valid;
+    };
+    std::vector<Group> groups;
+    cudaEvent_t ev_fork = nullptr;
+    int groups_req = 0;                    // ModeCtx::lane_groups at allocation time
     std::vector<float> gains;              // per-level gains of the current frame (member: no per-frame allocation)
 
     void reset();
@@ -108,6 +126,9 @@ struct MotionMode {
 
 private:
     mc_status allocate(const ModeCtx& ctx, const FrameIO& io, int levels);
+    mc_status make_groups(const ModeCtx& ctx);
+    void drop_groups();
+    mc_status run_group(const ModeCtx& ctx, const FrameIO& io, const mc_params& p, Group& g, bool first, double c_lo, double c_hi);
 };
 
 struct ColorMode {

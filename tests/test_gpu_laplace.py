@@ -387,6 +387,28 @@ def test_strip_egress_equals_tile_egress(w, h, c, lv):
             assert np.array_equal(a.float_output(w, h, c), b.float_output(w, h, c)), (w, h, t)
 
 
+@pytest.mark.parametrize("lanes,groups", [(8, 4), (5, 2), (3, 3), (16, 0), (2, 8)])
+def test_lane_groups_equal_single_chain(lanes, groups):
+    """Option lane_groups: the lanes of a handle run as several concurrent launch chains on their own CUDA streams (fork
+    from / join into the handle's stream).  Every lane must come out bit-identical to the single-chain run — outputs,
+    state planes, also after the group count changes mid-stream (state is kept) and through the pipelined host API."""
+    w, h, lv = 200, 136, 4
+    cfg, _ = make_cfgs(O.MODE_LAPLACE, 20, 50.0, 0.4, 3.0, 30, lv)
+    a, b = L.MagnificationProcessor(0, lanes=lanes), L.MagnificationProcessor(0, lanes=lanes)
+    a.set_option("lane_groups", 1)
+    b.set_option("lane_groups", groups)
+    for t in range(6):
+        f = np.stack([np.roll(synth_frame(t, w, h, 3), (3 * k, 7 * k), axis=(0, 1)) for k in range(lanes)])
+        if t == 4:
+            b.set_option("lane_groups", 2 if groups != 2 else 1)       # regroup mid-stream: temporal state must survive
+        _, oa = a.process_image(f, cfg)
+        _, ob = b.process_image(f, cfg)
+        assert np.array_equal(oa, ob), (lanes, groups, t)
+    for lvl in range(1, lv):
+        for name in ("lowpassHi", "lowpassLo"):
+            assert np.array_equal(a.get_state(name, lvl), b.get_state(name, lvl)), (lvl, name)
+
+
 def test_ingest_warps_option_equals_default():
     """Option ingest_warps (CTA shape of the fused BGR->Lab ingest kernel) must not change a bit: outputs and state,
     interior and ragged strips (widths around the 120-column strip size), odd heights."""
