@@ -164,7 +164,7 @@ void* mc_stream(mc_handle* h);
  *   "prefetch_state" (default 1; needs use_tma): the fused level kernel requests the tile's two state planes as TMA
  *        bulk copies at kernel entry, together with its input window, instead of loading them in its last phase
  *        (same results; measured on B200: level[1] 235 -> 205 us per 32-lane launch; 0 kept for A/B measurements)
- *   "lane_groups" (default 0 = automatic: min(4, lanes / 4), at least 1): Laplace — the lanes of the handle run as
+ *   "lane_groups" (default 0 = automatic: min(2, lanes / 8), at least 1): Laplace — the lanes of the handle run as
  *        that many concurrent launch chains on separate CUDA streams, forked from and joined into mc_stream(); the
  *        L1-bound ingest, issue-bound egress and HBM-bound level kernels of different groups then share the SMs
  *        instead of running back to back (same results; profile_kernels forces 1)
