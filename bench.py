@@ -144,48 +144,114 @@ def cpu_arm():
     return (lambda f: proc.process(f, ocfg)), "port", f"cv2 {cv2.__version__} oracle restatement"
 
 
-def time_oracle(n_warm, n_frames):
-    """CPU baseline on frames of the same workload, all host threads -> (frames/s, cores, seconds, kind, what)."""
+def cpu_info():
+    model = "unknown"
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                model = line.split(":", 1)[1].strip()
+                break
+    except Exception:
+        pass
+    import cv2
+    build = [l.strip() for l in cv2.getBuildInformation().splitlines() if l.strip()][:6]
+    return {"model": model, "logical_cpus": os.cpu_count() or 1, "cv2": cv2.__version__, "cv2_build_head": build}
+
+
+def time_cpu_single(threads, n_warm, n_frames):
+    """BASELINE.md section 3 protocol: one stream, cv2.setNumThreads(threads), n_warm untimed frames, then n_frames timed
+    one by one -> median ms/frame.  -> dict"""
     import cv2
     from lvm_b200.synth import synth_frame
     process, kind, what = cpu_arm()
-    cores = os.cpu_count() or 1
-    cv2.setNumThreads(cores)
+    cv2.setNumThreads(threads)
     frames = [synth_frame(t, W, H, CH) for t in range(8)]
     for t in range(n_warm):
         process(frames[t % 8])
-    t0 = time.perf_counter()
+    ms = []
     for t in range(n_frames):
+        t0 = time.perf_counter()
         process(frames[(n_warm + t) % 8])
-    dt = time.perf_counter() - t0
-    return n_frames / dt, cores, dt, kind, what
+        ms.append((time.perf_counter() - t0) * 1e3)
+    med = statistics.median(ms)
+    return {"threads": threads, "warmup_frames": n_warm, "frames": n_frames, "median_ms_per_frame": med, "fps": 1e3 / med,
+            "mean_fps": n_frames / (sum(ms) * 1e-3), "kind": kind, "what": what}
+
+
+def _cpu_worker(idx, threads, n_warm, n_frames, ready_q, start_evt, out_q):
+    """One independent stream of the CPU arm in its own process (throughput mode, the like-for-like of the GPU arm's lanes)."""
+    try:
+        import cv2
+        from lvm_b200.synth import synth_frame
+        process, kind, what = cpu_arm()
+        cv2.setNumThreads(threads)
+        frames = [np.roll(synth_frame(t, W, H, CH), (11 * idx, 37 * idx), axis=(0, 1)) for t in range(4)]
+        for t in range(n_warm):
+            process(frames[t % 4])
+        ready_q.put(idx)
+        start_evt.wait()
+        t0 = time.perf_counter()               # CLOCK_MONOTONIC: comparable across processes
+        for t in range(n_frames):
+            process(frames[(n_warm + t) % 4])
+        out_q.put((idx, n_frames, t0, time.perf_counter(), kind, what))
+    except Exception as e:                      # a worker that dies must not hang the parent
+        ready_q.put(idx)
+        out_q.put((idx, 0, 0.0, 0.0, "failed", repr(e)))
+
+
+def time_cpu_multiprocess(procs, threads, n_warm, n_frames):
+    """procs independent streams x threads OpenCV threads each: aggregate frames / (last end - first start)."""
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    ready_q, out_q, start_evt = ctx.Queue(), ctx.Queue(), ctx.Event()
+    ws = [ctx.Process(target=_cpu_worker, args=(i, threads, n_warm, n_frames, ready_q, start_evt, out_q)) for i in range(procs)]
+    for w in ws:
+        w.start()
+    for _ in ws:
+        ready_q.get(timeout=600)
+    start_evt.set()
+    res = [out_q.get(timeout=600) for _ in ws]
+    for w in ws:
+        w.join(timeout=30)
+    ok = [r for r in res if r[1] > 0]
+    if not ok:
+        return {"processes": procs, "threads_each": threads, "failed": [r[5] for r in res][:2]}
+    span = max(r[3] for r in ok) - min(r[2] for r in ok)
+    total = sum(r[1] for r in ok)
+    return {"processes": len(ok), "threads_each": threads, "warmup_frames": n_warm, "frames_each": n_frames, "fps": total / span,
+            "seconds": span, "kind": ok[0][4], "what": ok[0][5]}
+
+
+def mp_shape(cores):
+    """Throughput mode of the CPU arm: OpenCV barely scales past a handful of threads on one 1080p frame, so the host's
+    cores are used as cores/4 independent streams of 4 threads each."""
+    threads = 4 if cores >= 8 else 1
+    return max(1, cores // threads), threads
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return None
     per_step = args.ref_frames_per_step
-    import cv2
-    from lvm_b200.synth import synth_frame
-    process, kind, what = cpu_arm()
     cores = os.cpu_count() or 1
-    cv2.setNumThreads(cores)
-    frames = [synth_frame(t, W, H, CH) for t in range(8)]
-    i = 0
-    for _ in range(args.warmup * per_step):
-        process(frames[i % 8]); i += 1
-    t0 = time.perf_counter()
-    for _ in range(args.steps * per_step):
-        process(frames[i % 8]); i += 1
-    dt = time.perf_counter() - t0
-    fps = args.steps * per_step / dt
-    sample = f"{args.steps} steps x {per_step} frames of the 1080p workload, {what}, {cores} threads"
+    procs, threads = mp_shape(cores)
+    # throughput mode (the like-for-like of the GPU arm's lanes): every step = per_step frames on each of procs streams
+    mpr = time_cpu_multiprocess(procs, threads, args.warmup * per_step, args.steps * per_step)
+    # latency mode (one stream, all threads) beside it
+    one = time_cpu_single(cores, min(8, args.warmup * per_step), min(64, args.steps * per_step))
+    fps = max(mpr.get("fps", 0.0), one["fps"])
+    dt = (mpr["seconds"] if mpr.get("fps", 0.0) >= one["fps"] else one["frames"] / one["mean_fps"])
+    kind, what = one["kind"], one["what"]
+    sample = (f"{args.steps} steps x {per_step} frames of the 1080p workload on each of {procs} independent streams x {threads} "
+              f"OpenCV threads ({what}); single stream on {cores} threads beside it")
     return json.dumps({
         "impl": "reference", "metric": "1080p frames/sec (Laplace, 6-level)", "value": fps, "unit": "frames/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "frames_per_step": per_step},
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample},
+        "config": {"workload": WORKLOAD, "frames_per_step": per_step * (procs if mpr.get("fps", 0.0) >= one["fps"] else 1),
+                   "mode": "throughput: independent streams over all host cores (the GPU arm steps `lanes` independent streams)"},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample,
+                         "multi_process": mpr, "single_stream_all_threads": one, "host": cpu_info()},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     })
@@ -348,6 +414,33 @@ def run_ours(args, rank, world, local_rank):
     if prev_affinity is not None:
         os.sched_setaffinity(0, prev_affinity)   # the CPU baseline below uses every host core again
 
+    # ---- the call the drop-in adapter makes: ONE stream, blocking mc_process, host frame in / host frame out ----
+    single = None
+    if rank == 0:
+        from lvm_b200.synth import synth_frame
+        sp = L.MagnificationProcessor(device=local_rank, lanes=1)
+        fr = [synth_frame(t, W, H, CH) for t in range(4)]
+        pin_in = [torch.from_numpy(f).pin_memory() for f in fr]
+        pin_out = torch.empty((H, W, CH), dtype=torch.uint8).pin_memory()
+        cfg1 = L.ProcessorConfig(magnification=L.toParams(L.MagUiValues(L.MagnificationMode.Laplace, UI["amplification"], UI["wavelength"],
+                                                                         UI["low"], UI["high"], UI["chroma"], UI["levels"], UI["fps"])))
+        for i in range(6):
+            sp.process_image(fr[i % 4], cfg1)
+        lat_pg, lat_pin = [], []
+        for i in range(40):
+            t0 = time.perf_counter()
+            sp.process_image(fr[i % 4], cfg1)                      # pageable numpy in, numpy out (what a cv::Mat frame is)
+            lat_pg.append(time.perf_counter() - t0)
+        for i in range(40):
+            t0 = time.perf_counter()
+            sp.submit(pin_in[i % 4].data_ptr(), W, H, CH, row, p, pin_out.data_ptr(), row)
+            sp.collect()                                           # pinned (mc_host_alloc-style) frames
+            lat_pin.append(time.perf_counter() - t0)
+        sp.close()
+        single = {"lanes": 1, "pageable_ms_median": statistics.median(lat_pg) * 1e3, "pinned_ms_median": statistics.median(lat_pin) * 1e3,
+                  "pageable_fps": 1.0 / statistics.median(lat_pg), "pinned_fps": 1.0 / statistics.median(lat_pin),
+                  "note": "blocking call per frame, copies included; what MagnificationProcessorB200::process does per cv::Mat"}
+
     # ---- per-kernel device time (roofline of the dominant kernel) -------------------------------
     roof = None
     if rank == 0:
@@ -362,16 +455,17 @@ def run_ours(args, rank, world, local_rank):
             step_dev(3 + i)
         prof = proc.profile_read()
         proc.set_option("profile_kernels", 0)
-        table, traffic = kernel_table(prof, lanes)
+        table, traffic = kernel_table(prof, lanes, band_from_state=True)   # the library default
         dom = table[0]
         fused = next(t for t in table if t["kernel"] == "level[1]")   # the fused Laplace-pyramid + IIR kernel
         roof = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["algorithmic_GBps"], "peak": peak,
                 "unit": "GB/s", "frac": dom["algorithmic_GBps"] / peak, "traffic": traffic.get(dom["kernel"]),
                 "peak_source": peak_src, "interface_frac": dom["interface_GBps"] / peak,
-                "bound_note": ("the step's largest kernel converts BGR->Lab with OpenCV's exact 33^3 LUT: it is L1-gather / "
-                               "issue bound (ncu: l1tex 70 %, dram 14 %), so its HBM fraction is low by construction; the "
-                               "HBM-bound kernel of the path is the fused per-level pyramid+IIR kernel reported under "
-                               "fused_level_kernel (interface_frac = bytes its interface moves / time / peak)"),
+                "bound_note": ("the step's largest kernels are the exact OpenCV colour conversions: BGR->Lab ingest is bound by "
+                               "the L1 data pipe (two divergent 32-byte LUT gathers per pixel; ncu: l1tex 82 %, dram 16 %), "
+                               "Lab->BGR egress by issue slots; their HBM fraction is low by construction.  The HBM-bound "
+                               "kernel of the path is the fused per-level pyramid+IIR kernel reported under fused_level_kernel "
+                               "(interface_frac = bytes its interface moves / time / peak)"),
                 "fused_level_kernel": {"kernel": "level[1]", "achieved": fused["algorithmic_GBps"],
                                        "frac": fused["algorithmic_GBps"] / peak,
                                        "interface_frac": fused["interface_GBps"] / peak,
@@ -383,9 +477,18 @@ def run_ours(args, rank, world, local_rank):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, cores, dt, kind, what = time_oracle(2, args.cpu_frames)
-        cpu = {"value": v, "unit": "frames/s", "cores": cores, "kind": kind,
-               "sample": f"{args.cpu_frames} frames of the same 1080p clip through the {what} ({dt:.1f} s)"}
+        # 8 warm-up + >= 64 timed frames, median, at 1 thread and at all threads; plus the
+        # throughput mode (independent streams over all cores) that corresponds to what the GPU arm measures
+        cores = os.cpu_count() or 1
+        allt = time_cpu_single(cores, 8, args.cpu_frames)
+        onet = time_cpu_single(1, 4, max(16, args.cpu_frames // 4))
+        procs, threads = mp_shape(cores)
+        mpr = time_cpu_multiprocess(procs, threads, 4, 16)
+        best = max(allt["fps"], mpr.get("fps", 0.0))
+        cpu = {"value": best, "unit": "frames/s", "cores": cores, "kind": allt["kind"],
+               "sample": (f"{allt['what']}: best of one stream on {cores} threads ({args.cpu_frames} frames, median) and "
+                          f"{procs} independent streams x {threads} threads (16 frames each)"),
+               "single_stream_all_threads": allt, "single_stream_1_thread": onet, "multi_process": mpr, "host": cpu_info()}
 
     line = None
     if rank == 0:
@@ -394,10 +497,12 @@ def run_ours(args, rank, world, local_rank):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "lanes_per_gpu": lanes, "frames_per_step": lanes * world,
-                       "clip_frames": T,
+                       "clip_frames": T, "options": args.opt,
+                       "device_io": "`value` is device-in / device-out (frames resident in HBM, the ceiling a decoder/encoder hand-off would see)",
                        "l2": f"inputs {T * frame_bytes / 1e6:.0f} MB + per-lane state cycle through > L2 (126 MB); no flush needed"},
             "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": frame_bytes,
-                    "d2h_bytes_per_step": frame_bytes, "pipeline_depth": depth, "numa": numa},
+                    "d2h_bytes_per_step": frame_bytes, "pipeline_depth": depth, "numa": numa,
+                    "single_stream_blocking": single},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
         })
     if dist:
@@ -431,7 +536,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--lanes", type=int, default=32, help="independent 1080p streams per GPU, stepped in lock-step")
     ap.add_argument("--clip-frames", type=int, default=8)
-    ap.add_argument("--cpu-frames", type=int, default=48)
+    ap.add_argument("--cpu-frames", type=int, default=64)
     ap.add_argument("--ref-frames-per-step", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--opt", action="append", default=[], help="library option key=value (mc_set_option), repeatable")

@@ -105,7 +105,7 @@ def test_product_arm_dry_run_on_emulation(monkeypatch):
     monkeypatch.setitem(bench.UI, "levels", 4)
     try:
         args = types.SimpleNamespace(gpus=1, steps=3, warmup=3, lanes=2, clip_frames=2, cpu_frames=2, no_cpu_baseline=False,
-                                     ref_frames_per_step=1)
+                                     ref_frames_per_step=1, opt=[])
         d = json.loads(bench.run_ours(args, 0, 1, 0))
     finally:
         capi.LIB_PATH, capi._lib = saved
