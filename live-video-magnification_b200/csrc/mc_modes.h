@@ -112,7 +112,6 @@ struct MotionMode {
         int lane0 = 0, lanes = 0;
         cudaStream_t stream = nullptr;     // null: the handle's stream (single group)
         cudaEvent_t done = nullptr;
-        cudaEvent_t ingest_done = nullptr, egress_done = nullptr;   // stage tokens: group g+1 starts that stage after them
         std::vector<TensorMapStorage> tmaps, tmaps_hi, tmaps_lo;   // per level: TMA descriptors of G[l] / hi[l] / lo[l] of this group's planes
         std::vector<char> tmap_valid;
     };
@@ -129,7 +128,7 @@ private:
     mc_status allocate(const ModeCtx& ctx, const FrameIO& io, int levels);
     mc_status make_groups(const ModeCtx& ctx);
     void drop_groups();
-    mc_status run_group(const ModeCtx& ctx, const FrameIO& io, const mc_params& p, Group& g, const Group* prev, bool first, double c_lo, double c_hi);
+    mc_status run_group(const ModeCtx& ctx, const FrameIO& io, const mc_params& p, Group& g, bool first, double c_lo, double c_hi);
 };
 
 struct ColorMode {

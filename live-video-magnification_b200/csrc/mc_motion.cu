@@ -36,8 +36,6 @@ void MotionMode::drop_groups() {
     for (Group& g : groups) {
         if (g.stream) { cudaStreamSynchronize(g.stream); cudaStreamDestroy(g.stream); }
         if (g.done) cudaEventDestroy(g.done);
-        if (g.ingest_done) cudaEventDestroy(g.ingest_done);
-        if (g.egress_done) cudaEventDestroy(g.egress_done);
     }
     groups.clear();
     if (ev_fork) { cudaEventDestroy(ev_fork); ev_fork = nullptr; }
@@ -71,8 +69,6 @@ mc_status MotionMode::make_groups(const ModeCtx& ctx) {
         if (ng > 1) {
             MCK(cudaStreamCreateWithFlags(&grp.stream, cudaStreamNonBlocking));
             MCK(cudaEventCreateWithFlags(&grp.done, cudaEventDisableTiming));
-            MCK(cudaEventCreateWithFlags(&grp.ingest_done, cudaEventDisableTiming));
-            MCK(cudaEventCreateWithFlags(&grp.egress_done, cudaEventDisableTiming));
         }
         // TMA descriptors for the f32 inputs and the state planes of the fused level kernels, over this group's planes
         const size_t p0 = (size_t)grp.lane0 * channels;
@@ -148,22 +144,17 @@ mc_status MotionMode::process(const ModeCtx& ctx, const FrameIO& io, const mc_pa
     if (c_lo == 0) c_lo = 0.01;  // TemporalFilter.cpp:11-12
 
     if (groups.size() == 1) {
-        const mc_status st = run_group(ctx, io, p, groups[0], nullptr, first, c_lo, c_hi);
+        const mc_status st = run_group(ctx, io, p, groups[0], first, c_lo, c_hi);
         if (st != MC_OK) return st;
     } else {
         // fork: every group's chain starts after whatever the caller queued on the handle's stream (the frame upload),
         // join: the handle's stream continues after all of them (the download / the caller's next use of `out`)
         MCK(cudaEventRecord(ev_fork, ctx.stream));
-        // The chains are staggered on purpose: a group starts its ingest when the previous group's ingest is done, and
-        // its egress after the previous group's egress, so that at any moment the SMs hold DIFFERENT stages of different
-        // groups (ingest || level kernels || egress) rather than four copies of the same stage.
-        const Group* prev = nullptr;
         for (Group& g : groups) {
             MCK(cudaStreamWaitEvent(g.stream, ev_fork, 0));
             ModeCtx gctx = ctx;
             gctx.stream = g.stream;
-            const mc_status st = run_group(gctx, io, p, g, prev, first, c_lo, c_hi);
-            prev = &g;
+            const mc_status st = run_group(gctx, io, p, g, first, c_lo, c_hi);
             if (st != MC_OK) return st;
             MCK(cudaEventRecord(g.done, g.stream));
             MCK(cudaStreamWaitEvent(ctx.stream, g.done, 0));
@@ -179,7 +170,7 @@ mc_status MotionMode::process(const ModeCtx& ctx, const FrameIO& io, const mc_pa
 }
 
 // One group's launch set for one frame: lanes [g.lane0, g.lane0 + g.lanes) on ctx.stream.
-mc_status MotionMode::run_group(const ModeCtx& ctx, const FrameIO& io_all, const mc_params& p, Group& g, const Group* prev, bool first, double c_lo, double c_hi) {
+mc_status MotionMode::run_group(const ModeCtx& ctx, const FrameIO& io_all, const mc_params& p, Group& g, bool first, double c_lo, double c_hi) {
     FrameIO io = io_all;
     io.in = io_all.in + (size_t)g.lane0 * io_all.in_lane_stride;
     io.out = io_all.out + (size_t)g.lane0 * io_all.out_lane_stride;
@@ -193,11 +184,8 @@ mc_status MotionMode::run_group(const ModeCtx& ctx, const FrameIO& io_all, const
     // ingest: u8 BGR -> Lab16 planes (gray frames are read directly by the level-0 kernel)
     // (production path, >= 2 levels: one fused kernel also builds G1; otherwise Lab16 alone)
     const bool fused_ingest = channels == 3 && !faithful && levels >= 2;
-    if (prev && prev->ingest_done) MCK(cudaStreamWaitEvent(ctx.stream, prev->ingest_done, 0));
     if (fused_ingest) LAUNCH("ingest_lab", 0, launch_ingest_lab(io, *ctx.tables, lab, pitch16, plane16, off(G[1], 1), lv[1], ctx.stream, ctx.ingest_warps));
     else if (channels == 3) LAUNCH("lab16", 0, launch_lab16(io, *ctx.tables, lab, pitch16, plane16, ctx.stream));
-
-    if (g.ingest_done) MCK(cudaEventRecord(g.ingest_done, ctx.stream));
 
     // analysis: one fused kernel per level (level 0 only builds G1 unless the faithful option is on)
     const int l_begin = fused_ingest ? 1 : ((levels >= 2 || faithful) ? 0 : levels);
@@ -254,10 +242,8 @@ mc_status MotionMode::run_group(const ModeCtx& ctx, const FrameIO& io_all, const
     }
     const Level& l1 = lv[levels >= 1 ? 1 : 0];
     const Level& l2 = lv[levels >= 2 ? 2 : 0];
-    if (prev && prev->egress_done) MCK(cudaStreamWaitEvent(ctx.stream, prev->egress_done, 0));
     LAUNCH("egress", 0, launch_egress(io, *ctx.tables, lab, pitch16, plane16, m1, l1, c2, l2, (float)p.chromAttenuation, fout,
                                       ctx.stream, ctx.egress_strip));
-    if (g.egress_done) MCK(cudaEventRecord(g.egress_done, ctx.stream));
     return MC_OK;
 }
 
