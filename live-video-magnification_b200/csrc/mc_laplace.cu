@@ -725,12 +725,15 @@ __device__ __forceinline__ EgressIn<1> egress_load<1>(const EgressArgs& a, int l
     return r;
 }
 
+// `up` holds the pyrUp tap sums BEFORE their 1/64 scale: the scale is exact, so it is folded into the add (L) and
+// into the chroma factor (a, b) without changing a bit.  q / f: the row's output pointers at column gx (f may be null).
 template <int C>
-__device__ __forceinline__ void egress_convert(const EgressArgs& a, int lane, int gy, int gx, const EgressIn<C>& in, const float (&up)[C][4]);
+__device__ __forceinline__ void egress_convert(const EgressArgs& a, uint8_t* q, float* f, int gx, const EgressIn<C>& in, const float (&up)[C][4]);
 template <>
-__device__ __forceinline__ void egress_convert<3>(const EgressArgs& a, int lane, int gy, int gx, const EgressIn<3>& in, const float (&up)[3][4]) {
+__device__ __forceinline__ void egress_convert<3>(const EgressArgs& a, uint8_t* q, float* f, int gx, const EgressIn<3>& in, const float (&up)[3][4]) {
     uint8_t o8[12];
     float of[12];
+    const float chroma64 = a.chroma * kInv64;
     const short vL[4] = {in.L.x, in.L.y, in.L.z, in.L.w}, vA[4] = {in.A.x, in.A.y, in.A.z, in.A.w}, vB[4] = {in.B.x, in.B.y, in.B.z, in.B.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -739,9 +742,9 @@ __device__ __forceinline__ void egress_convert<3>(const EgressArgs& a, int lane,
         float B = fmaf((float)vB[i], 1.0f / 64.0f, -128.0f);
         if (a.m1.a) {
             // a,b motion planes *= chromAttenuation, then output = input + motion (MagnifyCore.hpp:140-148)
-            L = __fadd_rn(L, up[0][i]);
-            A = __fadd_rn(A, __fmul_rn(up[1][i], a.chroma));   // the reference scales the plane, then adds
-            B = __fadd_rn(B, __fmul_rn(up[2][i], a.chroma));
+            L = __fmaf_rn(up[0][i], kInv64, L);
+            A = __fadd_rn(A, __fmul_rn(up[1][i], chroma64));   // the reference scales the plane, then adds
+            B = __fadd_rn(B, __fmul_rn(up[2][i], chroma64));
         }
         float ob, og, orr;
         lab_to_bgr_fast(L, A, B, a.coeffs, a.gtab, ob, og, orr);
@@ -750,7 +753,6 @@ __device__ __forceinline__ void egress_convert<3>(const EgressArgs& a, int lane,
         // convertTo reduce to a min with 255 (NaN -> 0 by the conversion itself)
         o8[3 * i] = unit01_to_u8(ob); o8[3 * i + 1] = unit01_to_u8(og); o8[3 * i + 2] = unit01_to_u8(orr);
     }
-    uint8_t* q = a.out + (size_t)lane * a.out_lane_stride + (size_t)gy * a.out_step + (size_t)gx * 3;
     if (gx + 4 <= a.w0 && ((reinterpret_cast<uintptr_t>(q) & 3) == 0)) {
 #pragma unroll
         for (int wd = 0; wd < 3; ++wd)
@@ -761,25 +763,23 @@ __device__ __forceinline__ void egress_convert<3>(const EgressArgs& a, int lane,
         for (int i = 0; i < 12; ++i)
             if (gx + i / 3 < a.w0) q[i] = o8[i];
     }
-    if (a.fout) {
-        float* f = a.fout + (((size_t)lane * a.h0 + gy) * a.w0 + gx) * 3;
+    if (f) {
 #pragma unroll
         for (int i = 0; i < 12; ++i)
             if (gx + i / 3 < a.w0) f[i] = of[i];
     }
 }
 template <>
-__device__ __forceinline__ void egress_convert<1>(const EgressArgs& a, int lane, int gy, int gx, const EgressIn<1>& in, const float (&up)[1][4]) {
+__device__ __forceinline__ void egress_convert<1>(const EgressArgs& a, uint8_t* q, float* f, int gx, const EgressIn<1>& in, const float (&up)[1][4]) {
     uint8_t o8[4];
     float of[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         float v = u8_to_unit((uint8_t)((in.g >> (8 * i)) & 0xff));
-        if (a.m1.a) v = __fadd_rn(v, up[0][i]);
+        if (a.m1.a) v = __fmaf_rn(up[0][i], kInv64, v);
         of[i] = v;
         o8[i] = unit_to_u8(v);
     }
-    uint8_t* q = a.out + (size_t)lane * a.out_lane_stride + (size_t)gy * a.out_step + gx;
     if (gx + 4 <= a.w0 && ((reinterpret_cast<uintptr_t>(q) & 3) == 0)) {
         *reinterpret_cast<uint32_t*>(q) = (uint32_t)o8[0] | ((uint32_t)o8[1] << 8) | ((uint32_t)o8[2] << 16) | ((uint32_t)o8[3] << 24);
     } else {
@@ -787,8 +787,7 @@ __device__ __forceinline__ void egress_convert<1>(const EgressArgs& a, int lane,
         for (int i = 0; i < 4; ++i)
             if (gx + i < a.w0) q[i] = o8[i];
     }
-    if (a.fout) {
-        float* f = a.fout + ((size_t)lane * a.h0 + gy) * a.w0 + gx;
+    if (f) {
 #pragma unroll
         for (int i = 0; i < 4; ++i)
             if (gx + i < a.w0) f[i] = of[i];
@@ -798,7 +797,9 @@ __device__ __forceinline__ void egress_convert<1>(const EgressArgs& a, int lane,
 template <int C>
 __device__ __forceinline__ void egress_pixels(const EgressArgs& a, int lane, int gy, int gx, const float (&up)[C][4]) {
     const EgressIn<C> in = egress_load<C>(a, lane, gy, gx);
-    egress_convert<C>(a, lane, gy, gx, in, up);
+    uint8_t* q = a.out + (size_t)lane * a.out_lane_stride + (size_t)gy * a.out_step + (size_t)gx * C;
+    float* f = a.fout ? a.fout + (((size_t)lane * a.h0 + gy) * a.w0 + gx) * C : nullptr;
+    egress_convert<C>(a, q, f, gx, in, up);
 }
 
 template <int C>
@@ -896,8 +897,8 @@ __global__ void __launch_bounds__(256) k_egress(const EgressArgs a) {
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                up[ch][0][i] = __fmul_rn(up3(e[0][i], e[1][i], e[2][i]), kInv64);
-                up[ch][1][i] = __fmul_rn(up2(e[1][i], e[2][i]), kInv64);
+                up[ch][0][i] = up3(e[0][i], e[1][i], e[2][i]);   // x 1/64 is applied (exactly) in egress_convert
+                up[ch][1][i] = up2(e[1][i], e[2][i]);
             }
         }
     }
@@ -924,6 +925,34 @@ __global__ void __launch_bounds__(256) k_egress(const EgressArgs a) {
 // cv::pyrUp: row pass first), so the two kernels agree bit for bit; pyrUp's border rule (s[-1] := s[1],
 // s[n] := s[n-1]) is applied to the shuffled / streamed neighbours.  The kernel is issue-bound (Lab2BGR), not HBM-bound.
 // ------------------------------------------------------------------------------------------------
+// input samples of one row from running pointers (strip kernel): the three Lab16 plane rows at byte/element offset `off`,
+// or four gray bytes of a row
+template <int C>
+__device__ __forceinline__ EgressIn<C> egress_rows3(const int16_t* const (&p)[C], size_t off);
+template <>
+__device__ __forceinline__ EgressIn<3> egress_rows3<3>(const int16_t* const (&p)[3], size_t off) {
+    EgressIn<3> r;
+    r.L = __ldg(reinterpret_cast<const short4*>(p[0] + off));
+    r.A = __ldg(reinterpret_cast<const short4*>(p[1] + off));
+    r.B = __ldg(reinterpret_cast<const short4*>(p[2] + off));
+    return r;
+}
+template <>
+__device__ __forceinline__ EgressIn<1> egress_rows3<1>(const int16_t* const (&)[1], size_t) { return EgressIn<1>{0}; }
+template <int C>
+__device__ __forceinline__ EgressIn<C> egress_row1(const uint8_t* row, int gx, int w0);
+template <>
+__device__ __forceinline__ EgressIn<1> egress_row1<1>(const uint8_t* row, int gx, int w0) {
+    EgressIn<1> r;
+    r.g = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        if (gx >= 0 && gx + i < w0) r.g |= (uint32_t)__ldg(row + gx + i) << (8 * i);
+    return r;
+}
+template <>
+__device__ __forceinline__ EgressIn<3> egress_row1<3>(const uint8_t*, int, int) { return EgressIn<3>{}; }
+
 constexpr int EG_ROWS = 64;   // output rows per warp (a multiple of 4)
 
 template <int C> struct StripM1 { float2 h[C], l[C]; };   // band-1 source of one cur_1 row at the lane's two columns
@@ -1093,28 +1122,62 @@ __global__ void __launch_bounds__(32, MINB) k_egress_strip(const EgressArgs a) {
         put_E(j0, E);
     }
     const int j_end = (f_end + 1) >> 1;
+    // Running row pointers (advanced once per iteration instead of rebuilt per access): band-1 source rows at the lane's
+    // level-1 columns, the input rows at the lane's output columns, the output row.
+    const size_t st1 = (size_t)a.l1.pitch, st16 = (size_t)a.pitch16;
+    const float* ph[C];
+    const float* pl[C];
+    const int16_t* pin[C];
+#pragma unroll
+    for (int ch = 0; ch < C; ++ch) {
+        const size_t ro = row1(j0 + 1);
+        ph[ch] = a.m1.a + base1[ch] + ro;
+        pl[ch] = from_state ? a.m1.b + base1[ch] + ro : ph[ch];
+        pin[ch] = C == 3 ? a.lab + (size_t)(lane * 3 + ch) * a.plane16 + (size_t)(2 * j0) * st16 + gxl : nullptr;
+    }
+    const uint8_t* pg = C == 1 ? a.in + (size_t)lane * a.in_lane_stride + (size_t)(2 * j0) * a.in_step : nullptr;   // gray input row
+    uint8_t* pq = a.out + (size_t)lane * a.out_lane_stride + (size_t)(2 * j0) * a.out_step + (size_t)gx * C;
+    int sm = slot(j0 - 1), s0 = slot(j0), sp = slot(j0 + 1);           // ring slots of cur_1 rows j-1, j, j+1
     for (int j = j0; j < j_end; ++j) {
         const int jn = j + 1;
+        const bool two = 2 * j + 1 < f_end;                            // the chunk may end on an even row
         // what this iteration consumes (requested into L1 by the previous one) ...
-        const StripM1<C> cm = ld_m1(jn);
+        StripM1<C> cm;
+#pragma unroll
+        for (int ch = 0; ch < C; ++ch) {
+            cm.h[ch] = __ldg(reinterpret_cast<const float2*>(ph[ch]));
+            cm.l[ch] = from_state ? __ldg(reinterpret_cast<const float2*>(pl[ch])) : make_float2(0.f, 0.f);
+        }
         StripH2<C> chh;
         if (!(jn & 1) && jn < h1) chh = ld_h2((jn >> 1) + 1);
         EgressIn<C> in0, in1;
-        if (px_owner) {
-            in0 = egress_load<C>(a, lane, 2 * j, gx);
-            in1 = egress_load<C>(a, lane, min(2 * j + 1, a.h0 - 1), gx);
+        if (C == 3) {
+            in0 = egress_rows3<C>(pin, 0);
+            in1 = egress_rows3<C>(pin, two ? st16 : 0);
+        } else {
+            in0 = egress_row1<C>(pg, gx, a.w0);
+            in1 = egress_row1<C>(two ? pg + a.in_step : pg, gx, a.w0);
         }
         // ... and the requests for the next one: cur_1 row j+2, the level-2 row that enters the window with it, the inputs
         if (jn < j_end) {
-            pf_m1(jn + 1);
+            const bool adv1 = jn + 1 < h1;
             if (jn & 1) pf_h2(((jn + 1) >> 1) + 1);
-            pf_in(min(2 * jn, a.h0 - 1));
-            pf_in(min(2 * jn + 1, a.h0 - 1));
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch) {
+                if (adv1) { ph[ch] += st1; pl[ch] += st1; }
+                prefetch_l1(ph[ch]);
+                if (from_state) prefetch_l1(pl[ch]);
+                if (C == 3) {
+                    pin[ch] += 2 * st16;
+                    prefetch_l1(pin[ch]);
+                    if (2 * jn + 1 < a.h0) prefetch_l1(pin[ch] + st16);
+                }
+            }
+            if (C == 1) { pg += 2 * a.in_step; prefetch_l1(pg + gxl); }
         }
         // row j+1 of cur_1 (or its border copy) -> Ep
         float Ep[C][4];
         if (jn >= h1) {
-            const int s0 = slot(j);
 #pragma unroll
             for (int ch = 0; ch < C; ++ch) {
                 const float4 e = sE[s0][ch][lane_id];
@@ -1124,29 +1187,35 @@ __global__ void __launch_bounds__(32, MINB) k_egress_strip(const EgressArgs a) {
             if (!(jn & 1)) expand_h2(chh, (jn >> 1) + 1);     // an even row moves the level-2 window to centre jn / 2
             cur1_row(cm, jn, Ep);
         }
-        put_E(jn, Ep);
-        if (j == 0) put_E(-1, Ep);                            // cur_1[-1] := cur_1[1]
+#pragma unroll
+        for (int ch = 0; ch < C; ++ch) sE[sp][ch][lane_id] = make_float4(Ep[ch][0], Ep[ch][1], Ep[ch][2], Ep[ch][3]);
+        if (j == 0) {                                         // cur_1[-1] := cur_1[1]
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch) sE[sm][ch][lane_id] = make_float4(Ep[ch][0], Ep[ch][1], Ep[ch][2], Ep[ch][3]);
+        }
         if (px_owner) {
-            const int sm = slot(j - 1), s0 = slot(j);
             float up[C][4], t0[C][4];
 #pragma unroll
             for (int ch = 0; ch < C; ++ch) {
                 const float4 em = sE[sm][ch][lane_id], e0 = sE[s0][ch][lane_id];
                 t0[ch][0] = e0.x; t0[ch][1] = e0.y; t0[ch][2] = e0.z; t0[ch][3] = e0.w;
-                up[ch][0] = __fmul_rn(up3(em.x, e0.x, Ep[ch][0]), kInv64);
-                up[ch][1] = __fmul_rn(up3(em.y, e0.y, Ep[ch][1]), kInv64);
-                up[ch][2] = __fmul_rn(up3(em.z, e0.z, Ep[ch][2]), kInv64);
-                up[ch][3] = __fmul_rn(up3(em.w, e0.w, Ep[ch][3]), kInv64);
+                up[ch][0] = up3(em.x, e0.x, Ep[ch][0]);
+                up[ch][1] = up3(em.y, e0.y, Ep[ch][1]);
+                up[ch][2] = up3(em.z, e0.z, Ep[ch][2]);
+                up[ch][3] = up3(em.w, e0.w, Ep[ch][3]);
             }
-            egress_convert<C>(a, lane, 2 * j, gx, in0, up);
-            if (2 * j + 1 < f_end) {
+            float* f = a.fout ? a.fout + (((size_t)lane * a.h0 + 2 * j) * a.w0 + gx) * C : nullptr;
+            egress_convert<C>(a, pq, f, gx, in0, up);
+            if (two) {
 #pragma unroll
                 for (int ch = 0; ch < C; ++ch)
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) up[ch][i] = __fmul_rn(up2(t0[ch][i], Ep[ch][i]), kInv64);
-                egress_convert<C>(a, lane, 2 * j + 1, gx, in1, up);
+                    for (int i = 0; i < 4; ++i) up[ch][i] = up2(t0[ch][i], Ep[ch][i]);
+                egress_convert<C>(a, pq + a.out_step, f ? f + (size_t)a.w0 * C : nullptr, gx, in1, up);
             }
         }
+        pq += 2 * a.out_step;
+        const int t = sm; sm = s0; s0 = sp; sp = t;
     }
 }
 
