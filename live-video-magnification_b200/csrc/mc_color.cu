@@ -69,28 +69,49 @@ __global__ void k_mask_mul(float2* __restrict__ spec, size_t S, int nbins, int n
 }
 
 // per-lane min/max over `nchunks` chunks of `chunk` contiguous floats (chunk t at base + t*chunk_stride + lane*chunk)
-__global__ void k_minmax(const float* __restrict__ base, size_t chunk, int nchunks, size_t chunk_stride,
-                         unsigned* __restrict__ mm) {
-    const int lane = blockIdx.y;
-    float mn = INFINITY, mx = -INFINITY;
-    const size_t total = chunk * (size_t)nchunks;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const size_t t = i / chunk, r = i - t * chunk;
-        const float v = base[t * chunk_stride + (size_t)lane * chunk + r];
-        mn = fminf(mn, v);
-        mx = fmaxf(mx, v);
-    }
+// Block-wide min/max -> one ordered-int atomic pair per CTA (a few hundred per launch instead of one per warp)
+__device__ __forceinline__ void block_minmax_commit(float mn, float mx, unsigned* __restrict__ mm2) {
+    __shared__ float s_mn[8], s_mx[8];
     for (int o = 16; o; o >>= 1) {
         mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
         mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     }
-    if ((threadIdx.x & 31) == 0) {
-        atomicMin(&mm[2 * lane], f2ord(mn));
-        atomicMax(&mm[2 * lane + 1], f2ord(mx));
+    const int warp = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) { s_mn[warp] = mn; s_mx[warp] = mx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < (int)(blockDim.x >> 5); ++i) { mn = fminf(mn, s_mn[i]); mx = fmaxf(mx, s_mx[i]); }
+        atomicMin(&mm2[0], f2ord(mn));
+        atomicMax(&mm2[1], f2ord(mx));
     }
 }
 
-// filtered column -> normalize(0,1,MINMAX) -> * alpha -> pitched planes (TemporalFilter.cpp:55, MagnifyCore.hpp:185-192)
+// min/max of one stream's part of the filtered window: nchunks contiguous runs of `chunk` floats, chunk_stride apart
+// (TemporalFilter.cpp:55); 128-bit loads when the runs are 16-byte aligned
+__global__ void __launch_bounds__(256) k_minmax(const float* __restrict__ base, size_t chunk, int nchunks, size_t chunk_stride,
+                                                unsigned* __restrict__ mm, int vec_ok) {
+    const int lane = blockIdx.y;
+    float mn = INFINITY, mx = -INFINITY;
+    for (int t = 0; t < nchunks; ++t) {
+        const float* __restrict__ p = base + (size_t)t * chunk_stride + (size_t)lane * chunk;
+        if (vec_ok) {
+            const float4* __restrict__ p4 = reinterpret_cast<const float4*>(p);
+            for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < chunk / 4; i += (size_t)gridDim.x * blockDim.x) {
+                const float4 v = __ldg(p4 + i);
+                mn = fminf(fminf(mn, fminf(v.x, v.y)), fminf(v.z, v.w));
+                mx = fmaxf(fmaxf(mx, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+            }
+        } else {
+            for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < chunk; i += (size_t)gridDim.x * blockDim.x) {
+                const float v = __ldg(p + i);
+                mn = fminf(mn, v);
+                mx = fmaxf(mx, v);
+            }
+        }
+    }
+    block_minmax_commit(mn, mx, mm + 2 * lane);
+}
+
 __global__ void k_select(const float* __restrict__ col, const unsigned* __restrict__ mm, int C, int w, int h,
                          float alpha, float* __restrict__ dst, int pitch, size_t plane, int planes) {
     const size_t n = (size_t)planes * h * w;
@@ -110,33 +131,46 @@ __global__ void k_select(const float* __restrict__ col, const unsigned* __restri
 // cv::pyrUp with the default destination size 2w x 2h (SpatialFilter.cpp:45)
 __global__ void __launch_bounds__(256) k_pyrup2x(Level ls, Level ld, const float* __restrict__ src,
                                                  float* __restrict__ dst) {
-    __shared__ float sD[10][34];
-    __shared__ float sU[10][64];
+    // tile = 64 x 32 destination pixels, thread = 4 x 2 block: the 34 x 18 source window (pyrUp's border rule applied to
+    // the indices) goes to shared memory once, the row pass and the column pass run in registers, 128-bit stores
+    __shared__ __align__(16) float sD[18][36];
     const int plane = blockIdx.z;
-    const int x0 = blockIdx.x * 64, y0 = blockIdx.y * 16;
+    const int x0 = blockIdx.x * 64, y0 = blockIdx.y * 32;
     const float* __restrict__ s = src + (size_t)plane * ls.plane;
-    for (int idx = threadIdx.x; idx < 10 * 34; idx += blockDim.x) {
+    for (int idx = threadIdx.x; idx < 18 * 34; idx += 256) {
         const int k = idx / 34, j = idx - k * 34;
         const int iy = upsrc(y0 / 2 - 1 + k, ls.h), ix = upsrc(x0 / 2 - 1 + j, ls.w);
         sD[k][j] = __ldg(s + (size_t)iy * ls.pitch + ix);
     }
     __syncthreads();
-    for (int idx = threadIdx.x; idx < 10 * 64; idx += blockDim.x) {
-        const int k = idx / 64, x = idx - k * 64;
-        const int j0 = (x >> 1) + 1;
-        sU[k][x] = (x & 1) ? (sD[k][j0] + sD[k][j0 + 1]) * 4.0f : (sD[k][j0 - 1] + sD[k][j0] * 6.0f + sD[k][j0 + 1]);
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int gx = x0 + 4 * tx;
+    if (gx >= ld.w) return;
+    float e[3][4];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        const float2 p0 = *reinterpret_cast<const float2*>(&sD[ty + q][2 * tx]);
+        const float2 p1 = *reinterpret_cast<const float2*>(&sD[ty + q][2 * tx + 2]);
+        e[q][0] = __fadd_rn(__fmaf_rn(p0.y, 6.0f, p0.x), p1.x);
+        e[q][1] = __fmul_rn(__fadd_rn(p0.y, p1.x), 4.0f);
+        e[q][2] = __fadd_rn(__fmaf_rn(p1.x, 6.0f, p0.y), p1.y);
+        e[q][3] = __fmul_rn(__fadd_rn(p1.x, p1.y), 4.0f);
     }
-    __syncthreads();
     float* __restrict__ d = dst + (size_t)plane * ld.plane;
-    for (int idx = threadIdx.x; idx < 16 * 64; idx += blockDim.x) {
-        const int y = idx / 64, x = idx - y * 64;
-        const int gy = y0 + y, gx = x0 + x;
-        if (gy >= ld.h || gx >= ld.w) continue;
-        const int k0 = (y >> 1) + 1;
-        d[(size_t)gy * ld.pitch + gx] = (y & 1) ? ((sU[k0][x] + sU[k0 + 1][x]) * 4.0f) * (1.0f / 64.0f)
-                                                 : (sU[k0 - 1][x] + sU[k0][x] * 6.0f + sU[k0 + 1][x]) * (1.0f / 64.0f);
+#pragma unroll
+    for (int ry = 0; ry < 2; ++ry) {
+        const int gy = y0 + 2 * ty + ry;
+        if (gy >= ld.h) continue;
+        float o[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            o[i] = ry ? __fmul_rn(__fmul_rn(__fadd_rn(e[1][i], e[2][i]), 4.0f), 1.0f / 64.0f)
+                      : __fmul_rn(__fadd_rn(__fmaf_rn(e[1][i], 6.0f, e[0][i]), e[2][i]), 1.0f / 64.0f);
+        // rows are padded to a multiple of 32 floats, so a full float4 at gx < w is always in-bounds
+        *reinterpret_cast<float4*>(d + (size_t)gy * ld.pitch + gx) = make_float4(o[0], o[1], o[2], o[3]);
     }
 }
+
 
 // cv::resize(INTER_LINEAR) on f32 planes (SpatialFilter.cpp:48): horizontal then vertical lerp
 __global__ void k_resize_linear(Level ls, Level ld, const float* __restrict__ src, float* __restrict__ dst) {
@@ -161,29 +195,32 @@ __global__ void k_resize_linear(Level ls, Level ld, const float* __restrict__ sr
 }
 
 // min/max of output = input + colorImg per lane (MagnifyCore.hpp:197-201)
-__global__ void k_sum_minmax(const float* __restrict__ a, const float* __restrict__ b, Level l, int C,
-                             unsigned* __restrict__ mm) {
+__global__ void __launch_bounds__(256) k_sum_minmax(const float* __restrict__ a, const float* __restrict__ b, Level l, int C,
+                                                    unsigned* __restrict__ mm) {
+    // one stream per blockIdx.y; the CTAs of a stream share its C * h rows, each row read as 128-bit vectors
     const int lane = blockIdx.y;
     float mn = INFINITY, mx = -INFINITY;
-    const size_t total = (size_t)C * l.h * l.w;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int c = (int)(i / ((size_t)l.h * l.w));
-        const int rem = (int)(i - (size_t)c * l.h * l.w);
-        const int y = rem / l.w, x = rem - y * l.w;
-        const size_t o = (size_t)(lane * C + c) * l.plane + (size_t)y * l.pitch + x;
-        const float v = a[o] + b[o];
-        mn = fminf(mn, v);
-        mx = fmaxf(mx, v);
+    const int rows = C * l.h, w4 = l.w >> 2;
+    for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+        const int c = r / l.h, y = r - c * l.h;
+        const size_t o = (size_t)(lane * C + c) * l.plane + (size_t)y * l.pitch;
+        const float4* __restrict__ a4 = reinterpret_cast<const float4*>(a + o);
+        const float4* __restrict__ b4 = reinterpret_cast<const float4*>(b + o);
+        for (int i = threadIdx.x; i < w4; i += 256) {
+            const float4 u = __ldg(a4 + i), v = __ldg(b4 + i);
+            const float s0 = u.x + v.x, s1 = u.y + v.y, s2 = u.z + v.z, s3 = u.w + v.w;
+            mn = fminf(fminf(mn, fminf(s0, s1)), fminf(s2, s3));
+            mx = fmaxf(fmaxf(mx, fmaxf(s0, s1)), fmaxf(s2, s3));
+        }
+        for (int x = 4 * w4 + threadIdx.x; x < l.w; x += 256) {
+            const float sv = __ldg(a + o + x) + __ldg(b + o + x);
+            mn = fminf(mn, sv);
+            mx = fmaxf(mx, sv);
+        }
     }
-    for (int o = 16; o; o >>= 1) {
-        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    }
-    if ((threadIdx.x & 31) == 0) {
-        atomicMin(&mm[2 * lane], f2ord(mn));
-        atomicMax(&mm[2 * lane + 1], f2ord(mx));
-    }
+    block_minmax_commit(mn, mx, mm + 2 * lane);
 }
+
 
 // out8u = convertTo(input + colorImg, 255/(max-min), -min*255/(max-min))  (MagnifyCore.hpp:202-203)
 template <int C>
@@ -415,9 +452,11 @@ mc_status ColorMode::process(const ModeCtx& ctx, const FrameIO& io, const mc_par
     ++*ctx.launches;
     {
         // global min/max per stream over all pixels, frames and channels (TemporalFilter.cpp:55)
-        dim3 grid(gs_blocks((size_t)C * small_rows * n) / 2 + 1, lanes);
+        const size_t chunk = (size_t)C * small_rows;
+        const int vec_ok = chunk % 4 == 0 && S % 4 == 0 && (reinterpret_cast<uintptr_t>(work) & 15) == 0;
+        dim3 grid((unsigned)std::max<size_t>(1, std::min<size_t>(chunk / 1024 + 1, (size_t)(592 / lanes + 1))), lanes);
         const bool pp = ctx.prof && ctx.prof->begin("minmax_window", 0, ctx.stream);
-        k_minmax<<<grid, 256, 0, ctx.stream>>>(work, (size_t)C * small_rows, n, S, mm);
+        k_minmax<<<grid, 256, 0, ctx.stream>>>(work, chunk, n, S, mm, vec_ok);
         if (pp) ctx.prof->end(ctx.stream);
         MCK(cudaGetLastError());
         ++*ctx.launches;
@@ -436,7 +475,7 @@ mc_status ColorMode::process(const ModeCtx& ctx, const FrameIO& io, const mc_par
     for (int i = 0; i < levels; ++i) {
         const Level& s0 = ulv[(size_t)i];
         const Level& d0 = ulv[(size_t)i + 1];
-        dim3 grid(cdiv(d0.w, 64), cdiv(d0.h, 16), planes);
+        dim3 grid(cdiv(d0.w, 64), cdiv(d0.h, 32), planes);
         const bool pp = ctx.prof && ctx.prof->begin("pyrup2x", i, ctx.stream);
         k_pyrup2x<<<grid, 256, 0, ctx.stream>>>(s0, d0, U[(size_t)i], U[(size_t)i + 1]);
         if (pp) ctx.prof->end(ctx.stream);
@@ -454,7 +493,7 @@ mc_status ColorMode::process(const ModeCtx& ctx, const FrameIO& io, const mc_par
         color_img = U[(size_t)levels + 1];
     }
     {
-        dim3 grid(gs_blocks((size_t)C * w * h) / 2 + 1, lanes);
+        dim3 grid((unsigned)std::max(1, std::min(C * h, 1184 / lanes + 1)), lanes);
         const bool pp = ctx.prof && ctx.prof->begin("minmax_out", 0, ctx.stream);
         k_sum_minmax<<<grid, 256, 0, ctx.stream>>>(G[0], color_img, lv[0], C, mm + 2 * lanes);
         if (pp) ctx.prof->end(ctx.stream);

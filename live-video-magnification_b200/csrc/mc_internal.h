@@ -58,8 +58,9 @@ struct FrameIO {
 };
 
 // u8 BGR frame -> Lab int16 planes [lanes*3][h][pitch16] (exact OpenCV LUT values)
+// (l_f32 != null: also the L plane as f32 [lanes][h][l_pitch] — Phase's input)
 cudaError_t launch_lab16(const FrameIO& io, const DeviceTables& tb, int16_t* lab, int pitch16, size_t plane16,
-                         cudaStream_t s);
+                         cudaStream_t s, float* l_f32 = nullptr, int l_pitch = 0, size_t l_plane = 0);
 
 // fused ingest of the production path: u8 BGR -> Lab16 planes + G1 = pyrDown(Lab) (MagnifyCore.hpp:87-96, level 0)
 cudaError_t launch_ingest_lab(const FrameIO& io, const DeviceTables& tb, int16_t* lab, int pitch16, size_t plane16,

@@ -88,7 +88,8 @@ __device__ __forceinline__ float band_of(float hi, float lo, float gain) { retur
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_lab16(const uint8_t* __restrict__ in, size_t in_step, size_t in_lane_stride,
                                                int w, int h, const LabLutCell* __restrict__ lut,
-                                               int16_t* __restrict__ lab, int pitch16, size_t plane16, int aligned) {
+                                               int16_t* __restrict__ lab, int pitch16, size_t plane16, int aligned,
+                                               float* __restrict__ lf, int lf_pitch, size_t lf_plane) {
     const int lane = blockIdx.z;
     const int y = blockIdx.y;
     const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
@@ -119,6 +120,11 @@ __global__ void __launch_bounds__(256) k_lab16(const uint8_t* __restrict__ in, s
     *reinterpret_cast<short4*>(o) = make_short4(L[0], L[1], L[2], L[3]);
     *reinterpret_cast<short4*>(o + plane16) = make_short4(A[0], A[1], A[2], A[3]);
     *reinterpret_cast<short4*>(o + 2 * plane16) = make_short4(B[0], B[1], B[2], B[3]);
+    if (lf) {   // Phase magnifies the L plane only (MagnifyCore.hpp:217-222): emit it as f32 too (rows padded to 32 floats)
+        const float k = 100.0f / 16384.0f;
+        *reinterpret_cast<float4*>(lf + (size_t)lane * lf_plane + (size_t)y * lf_pitch + x) =
+            make_float4((float)L[0] * k, (float)L[1] * k, (float)L[2] * k, (float)L[3] * k);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1262,10 +1268,10 @@ bool make_level_tensor_map(void* out_map, const float* base, const Level& l, int
 }
 
 cudaError_t launch_lab16(const FrameIO& io, const DeviceTables& tb, int16_t* lab, int pitch16, size_t plane16,
-                         cudaStream_t s) {
+                         cudaStream_t s, float* l_f32, int l_pitch, size_t l_plane) {
     const int aligned = (reinterpret_cast<uintptr_t>(io.in) % 4 == 0) && (io.in_step % 4 == 0) && (io.in_lane_stride % 4 == 0);
     dim3 grid(cdiv(cdiv(io.w, 4), 256), io.h, io.lanes);
-    k_lab16<<<grid, 256, 0, s>>>(io.in, io.in_step, io.in_lane_stride, io.w, io.h, tb.lab_lut, lab, pitch16, plane16, aligned);
+    k_lab16<<<grid, 256, 0, s>>>(io.in, io.in_step, io.in_lane_stride, io.w, io.h, tb.lab_lut, lab, pitch16, plane16, aligned, l_f32, l_pitch, l_plane);
     return cudaGetLastError();
 }
 

@@ -51,14 +51,6 @@ __device__ __forceinline__ float mulr(float a, float b) { return __fmul_rn(a, b)
 __device__ __forceinline__ float addr(float a, float b) { return __fadd_rn(a, b); }
 __device__ __forceinline__ float subr(float a, float b) { return __fsub_rn(a, b); }
 
-__global__ void k_s16_to_f32(const int16_t* __restrict__ src, int pitch16, size_t plane16, int plane_step,
-                             float scale, float off, Level l, float* __restrict__ dst) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, lane = blockIdx.z;
-    if (x >= l.w) return;
-    const float v = (float)src[(size_t)lane * plane_step * plane16 + (size_t)y * pitch16 + x];
-    dst[(size_t)lane * l.plane + (size_t)y * l.pitch + x] = fmaf(v, scale, off);
-}
-
 // 9x9 kernels are register-blocked: a thread owns a 1x4 strip, loads 12 tile values per kernel row with three
 // 128-bit shared-memory reads and issues 36 FMAs on them.  Rows are dealt to warps so that both rows of a
 // warp have the same parity (the sub-sampled low-pass / the zero-injected up-sampling only touch one parity),
@@ -500,11 +492,7 @@ mc_status RieszMode::process(const ModeCtx& ctx, const FrameIO& io, const mc_par
         allocated = true;
     }
     // BGR -> Lab; only L is magnified (MagnifyCore.hpp:217-222)
-    LAUNCH("lab16", 0, launch_lab16(io, *ctx.tables, lab16, pitch16, plane16, ctx.stream));
-    {
-        dim3 grid(cdiv(w, 256), h, lanes);
-        KLAUNCH("L_plane", 0, k_s16_to_f32<<<grid, 256, 0, ctx.stream>>>(lab16, pitch16, plane16, 3, 100.0f / 16384.0f, 0.0f, lv[0], oct[0]));
-    }
+    LAUNCH("lab16", 0, launch_lab16(io, *ctx.tables, lab16, pitch16, plane16, ctx.stream, oct[0], lv[0].pitch, lv[0].plane));
     mc_status st = build_pyramid(ctx);
     if (st != MC_OK) return st;
     if (first) {
