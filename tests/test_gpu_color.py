@@ -67,6 +67,24 @@ def test_color_lanes_match_single():
                 assert int(u8_diff(mo[k], outs[k][1]).max()) <= 1
 
 
+def test_color_more_than_64_lanes():
+    """Handles with more than 64 lanes: every lane's min/max slots must be initialised (round-1 advisor finding: k_mm_init
+    covered only the first 256 slots, lane 69 of 70 came out 255 LSB off) — the last lanes equal a 1-lane handle."""
+    w, h, lanes, n = 64, 48, 70, 5
+    cfg, _ = make_cfgs(O.MODE_COLOR, 100, 0.0, 0.8, 1.2, 0, 2, 30.0)
+    many = L.MagnificationProcessor(0, lanes=lanes)
+    singles = {k: L.MagnificationProcessor(0) for k in (0, 64, 69)}
+    for t in range(n):
+        base = synth_frame(t, w, h, 3)
+        frames = np.stack([np.roll(base, (k, 2 * k), axis=(0, 1)) for k in range(lanes)])
+        produced, outs = many.process_image(frames, cfg)
+        for k, p1 in singles.items():
+            prod1, o1 = p1.process_image(frames[k], cfg)
+            assert prod1 == produced
+            if produced:
+                assert np.array_equal(outs[k], o1), (t, k)
+
+
 def test_color_framerate_changes_keep_window_semantics():
     """framerate is a live parameter: the window cap getOptimalBufferSize(int(fps)) grows (16 -> 64) and shrinks
     (64 -> 16, also while the ring is only partly filled) without a reset; the DFT length follows the window."""
