@@ -39,8 +39,8 @@ def test_product_arm_needs_a_gpu():
 
 def test_kernel_table_accounting():
     """bench.kernel_table: interface / algorithmic byte models per kernel (no GPU needed), for the default data flow
-    (level kernels store their band) and for option band_from_state; ncu captures are only quoted for kernels whose
-    interface still matches the capture."""
+    (level kernels store their band, option band_from_state = 0) and for the shipped default band_from_state = 1; ncu
+    captures are only quoted for kernels whose interface still matches the capture."""
     sys.path.insert(0, ROOT)
     import bench
     px = bench.level_pixels(1920, 1080, 6)
@@ -54,14 +54,14 @@ def test_kernel_table_accounting():
     assert by["egress[0]"]["interface_bytes"] == 32 * 3 * (3 * px[0] + 4 * px[1] + 4 * px[2])
     assert abs(by["level[1]"]["algorithmic_GBps"] - 16 * 3 * px[1] * 32 / 200e-6 / 1e9) < 1e-6
     assert abs(sum(t["share"] for t in table) - 1.0) < 1e-9
-    assert {"ingest_lab[0]", "egress[0]", "level[1]"} <= set(traffic)               # captures match this data flow
+    assert "ingest_lab[0]" in traffic and "level[1]" not in traffic and "egress[0]" not in traffic   # captures are of the shipped flow
     table2, traffic2 = bench.kernel_table(prof, 32, band_from_state=True)
     by2 = {t["kernel"]: t for t in table2}
     assert by2["level[1]"]["interface_bytes"] == 32 * 3 * (16 * px[1] + 4 * px[1] + 4 * px[2])
     assert by2["collapse[2]"]["interface_bytes"] == 32 * 3 * (12 * px[2] + 4 * px[3])
     assert by2["collapse[4]"]["interface_bytes"] == 32 * 3 * (12 * px[4] + 8 * px[5])  # top band comes from state planes
     assert by2["egress[0]"]["interface_bytes"] == 32 * 3 * (3 * px[0] + 8 * px[1] + 4 * px[2])
-    assert "level[1]" not in traffic2 and "egress[0]" not in traffic2                # stale for that data flow
+    assert {"ingest_lab[0]", "egress[0]", "level[1]", "level[2]"} <= set(traffic2)  # round-2 captures: band rebuilt from state
 
 
 @pytest.mark.emu
@@ -105,7 +105,7 @@ def test_product_arm_dry_run_on_emulation(monkeypatch):
     monkeypatch.setitem(bench.UI, "levels", 4)
     try:
         args = types.SimpleNamespace(gpus=1, steps=3, warmup=3, lanes=2, clip_frames=2, cpu_frames=2, no_cpu_baseline=False,
-                                     ref_frames_per_step=1, opt=[])
+                                     ref_frames_per_step=1, opt=[], workload="1080p6")
         d = json.loads(bench.run_ours(args, 0, 1, 0))
     finally:
         capi.LIB_PATH, capi._lib = saved
