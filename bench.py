@@ -535,7 +535,7 @@ def main():
     ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--lanes", type=int, default=32, help="independent 1080p streams per GPU, stepped in lock-step")
+    ap.add_argument("--lanes", type=int, default=64, help="independent 1080p streams per GPU, stepped in lock-step")
     ap.add_argument("--clip-frames", type=int, default=8)
     ap.add_argument("--cpu-frames", type=int, default=64)
     ap.add_argument("--ref-frames-per-step", type=int, default=1)
@@ -549,8 +549,8 @@ def main():
         W, H, LEVELS = 3840, 2160, 8
         UI["levels"] = 8
         WORKLOAD = "Motion (Laplace) 3840x2160x3 BGR, 8 levels, IIR 0.4-3 Hz @30fps, alpha=20 (BASELINE.json configs[4])"
-        if args.lanes == 32:
-            args.lanes = 8           # 4 x the pixels per stream: the same bytes per step as 32 lanes of 1080p
+        if args.lanes == 64:
+            args.lanes = 16          # 4 x the pixels per stream: the same bytes per step as 64 lanes of 1080p
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
