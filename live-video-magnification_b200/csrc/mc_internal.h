@@ -88,6 +88,8 @@ struct LevelArgs {
 // 128-byte opaque CUtensorMap storage + encoder for the level kernel's (72 x 39 x 1) box
 struct alignas(64) TensorMapStorage { unsigned char bytes[128]; };
 bool make_level_tensor_map(void* out_map, const float* base, const Level& l, int planes, bool state_tile = false);
+// general form: box of box_w x box_h x 1 f32 elements (row bytes must be a multiple of 16)
+bool make_tensor_map_box(void* out_map, const float* base, const Level& l, int planes, int box_w, int box_h);
 // fused per level: pyrDown + pyrUp + subtract + dual-EMA update + gain (SpatialFilter.cpp:25-38,
 // TemporalFilter.cpp:9-22, MagnifyCore.hpp:127-134)
 cudaError_t launch_level(const LevelArgs& a, cudaStream_t s);

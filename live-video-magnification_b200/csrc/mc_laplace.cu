@@ -14,50 +14,11 @@
 #include <cuda.h>   // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
 
 #include "mc_internal.h"
+#include "mc_tma.cuh"
 
 namespace mc {
 
 namespace {
-
-// ---- TMA (cp.async.bulk.tensor) + mbarrier primitives -------------------------------------------
-#if defined(MC_CUDA_EMU)   // CPU logic emulation for GPU-less CI (tests/cuda_emu): same calls, emulated copy engine
-__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) { cuda_emu::mbar_init(bar, count); }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) { cuda_emu::mbar_expect_tx(bar, bytes); }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) { cuda_emu::mbar_wait(bar, parity); }
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, int x, int y, int z, uint64_t* bar) {
-    const int c[3] = {x, y, z};
-    cuda_emu::tma_load(dst, tm, c, bar);
-}
-#else
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");   // make the init visible to the async proxy
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
-    // try_wait suspends the thread for a hardware-defined time slice per attempt; a copy that has not landed after
-    // 2^22 attempts (seconds) never will — trap so a bad descriptor surfaces as a launch error, not as a hung GPU.
-    unsigned ok = 0;
-    for (unsigned spin = 0; spin < (1u << 22); ++spin) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-        if (ok) return;
-    }
-    __trap();
-}
-// 3-D tiled load {x, y, plane} -> shared; out-of-bounds elements are zero-filled by the TMA unit
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, int x, int y, int z, uint64_t* bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z) : "memory");
-}
-
-#endif
 
 // request a line into L1 ahead of its use (no register is tied up, unlike a load issued early)
 __device__ __forceinline__ void prefetch_l1(const void* p) {
@@ -1252,19 +1213,23 @@ static TensorMapEncodeFn tensor_map_encoder() {
     return fn;
 }
 
-// Encodes a 3-D tiled tensor map {w, h, planes} over pitched f32 planes with the level kernel's box.
-bool make_level_tensor_map(void* out_map, const float* base, const Level& l, int planes, bool state_tile) {
+// Encodes a 3-D tiled tensor map {w, h, planes} over pitched f32 planes with a box of box_w x box_h x 1 elements.
+bool make_tensor_map_box(void* out_map, const float* base, const Level& l, int planes, int box_w, int box_h) {
     const TensorMapEncodeFn encode = tensor_map_encoder();
     if (!encode) return false;
     const cuuint64_t dims[3] = {(cuuint64_t)l.w, (cuuint64_t)l.h, (cuuint64_t)planes};
     const cuuint64_t strides[2] = {(cuuint64_t)l.pitch * sizeof(float), (cuuint64_t)l.plane * sizeof(float)};
-    // input window (72 x 39, origin x0-4, y0-4) or state tile (64 x 32, origin x0, y0)
-    const cuuint32_t box[3] = {(cuuint32_t)(state_tile ? TW : GW), (cuuint32_t)(state_tile ? TH : GH), 1u};
+    const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1u};
     const cuuint32_t estr[3] = {1u, 1u, 1u};
     const CUresult r = encode(reinterpret_cast<CUtensorMap*>(out_map), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base),
                               dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
+}
+
+// the level kernel's boxes: input window (72 x 39, origin x0-4, y0-4) or state tile (64 x 32, origin x0, y0)
+bool make_level_tensor_map(void* out_map, const float* base, const Level& l, int planes, bool state_tile) {
+    return make_tensor_map_box(out_map, base, l, planes, state_tile ? TW : GW, state_tile ? TH : GH);
 }
 
 cudaError_t launch_lab16(const FrameIO& io, const DeviceTables& tb, int16_t* lab, int pitch16, size_t plane16,

@@ -178,6 +178,9 @@ struct RieszMode {
     int16_t* lab16 = nullptr;
     int pitch16 = 0;
     size_t plane16 = 0;
+    // TMA descriptors of the 9x9 kernels' input tiles (72 x 24 boxes): octave i (analysis), amplified band i (collapse)
+    std::vector<TensorMapStorage> tm_oct, tm_band;
+    std::vector<char> tm_valid;
 
     void reset();
     mc_status process(const ModeCtx& ctx, const FrameIO& io, const mc_params& p, int levels, int* produced);

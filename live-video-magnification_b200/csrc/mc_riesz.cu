@@ -15,6 +15,7 @@
 #include <cstring>
 
 #include "mc_modes.h"
+#include "mc_tma.cuh"
 
 namespace mc {
 
@@ -63,9 +64,20 @@ __device__ __forceinline__ int r9_row(int tid) {     // tile row of this thread:
     return 4 * (w >> 1) + (w & 1) + 2 * half;
 }
 
-__device__ __forceinline__ void r9_load_tile(float (*s)[R9_SW], const float* __restrict__ src, const Level& l, int x0, int y0) {
+// Stages the (R9_SH x R9_SW) window of one plane, origin (x0-4, y0-4), BORDER_REFLECT_101.  Interior tiles with a
+// tensor map: ONE cp.async.bulk.tensor copy issued by one thread, completion on an mbarrier (`bar` must have been
+// initialised and fenced by the caller before the block-wide barrier that precedes this call); otherwise 128-bit loads
+// (interior) or scalar reflected loads (tiles touching an image border).
+__device__ __forceinline__ void r9_load_tile(float (*s)[R9_SW], const float* __restrict__ src, const Level& l, int x0, int y0,
+                                             const CUtensorMap* tm = nullptr, int plane = 0, uint64_t* bar = nullptr) {
     const bool interior = x0 >= 4 && x0 + R9_W + 4 <= l.w && y0 >= 4 && y0 + R9_H + 4 <= l.h;
-    if (interior) {
+    if (interior && tm) {
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(bar, R9_SH * R9_SW * sizeof(float));
+            tma_load_3d(&s[0][0], tm, x0 - 4, y0 - 4, plane, bar);
+        }
+        mbar_wait(bar, 0);
+    } else if (interior) {
         for (int i = threadIdx.x; i < R9_SH * (R9_SW / 4); i += 256) {
             const int r = i / (R9_SW / 4), c4 = i - r * (R9_SW / 4);
             *reinterpret_cast<float4*>(&s[r][4 * c4]) =
@@ -81,11 +93,17 @@ __device__ __forceinline__ void r9_load_tile(float (*s)[R9_SW], const float* __r
 
 // hp = filter2D(oct, HP) ; next = subsample(filter2D(oct, 2*LP))   (REFLECT_101, correlation)
 __global__ void __launch_bounds__(256) k_riesz_analysis(Level l, Level ln, const float* __restrict__ oct,
-                                                        float* __restrict__ hp, float* __restrict__ next) {
-    __shared__ __align__(16) float s[R9_SH][R9_SW];
+                                                        float* __restrict__ hp, float* __restrict__ next,
+                                                        const __grid_constant__ CUtensorMap tm, int use_tma) {
+    __shared__ __align__(128) float s[R9_SH][R9_SW];
+    __shared__ __align__(8) uint64_t bar;
     const int plane = blockIdx.z;
     const int x0 = blockIdx.x * R9_W, y0 = blockIdx.y * R9_H;
-    r9_load_tile(s, oct + (size_t)plane * l.plane, l, x0, y0);
+    if (use_tma) {
+        if (threadIdx.x == 0) mbar_init(&bar, 1);
+        __syncthreads();
+    }
+    r9_load_tile(s, oct + (size_t)plane * l.plane, l, x0, y0, use_tma ? &tm : nullptr, plane, &bar);
     __syncthreads();
     const int tx = threadIdx.x & 15, y = r9_row(threadIdx.x);
     const int gy = y0 + y, gx = x0 + 4 * tx;
@@ -352,12 +370,18 @@ __device__ __forceinline__ void rc_lowpass(const float (*sc)[RC_CW], int y, int 
 }
 
 __global__ void __launch_bounds__(256) k_riesz_collapse(Level l, Level lc, const float* __restrict__ band,
-                                                        const float* __restrict__ coarse, float* __restrict__ out) {
-    __shared__ __align__(16) float sb[R9_SH][R9_SW];
+                                                        const float* __restrict__ coarse, float* __restrict__ out,
+                                                        const __grid_constant__ CUtensorMap tm, int use_tma) {
+    __shared__ __align__(128) float sb[R9_SH][R9_SW];
     __shared__ __align__(16) float sc[RC_CH][RC_CW];
+    __shared__ __align__(8) uint64_t bar;
     const int plane = blockIdx.z;
     const int x0 = blockIdx.x * R9_W, y0 = blockIdx.y * R9_H;
-    r9_load_tile(sb, band + (size_t)plane * l.plane, l, x0, y0);
+    if (use_tma) {
+        if (threadIdx.x == 0) mbar_init(&bar, 1);
+        __syncthreads();
+    }
+    r9_load_tile(sb, band + (size_t)plane * l.plane, l, x0, y0, use_tma ? &tm : nullptr, plane, &bar);
     const float* __restrict__ c = coarse + (size_t)plane * lc.plane;
     for (int i = threadIdx.x; i < RC_CH * RC_CW; i += 256) {
         const int r = i / RC_CW, cc = i - r * RC_CW;
@@ -438,7 +462,9 @@ mc_status RieszMode::build_pyramid(const ModeCtx& ctx) {
     for (int i = 0; i < levels - 1; ++i) {
         const Level& l = lv[(size_t)i];
         dim3 grid(cdiv(l.w, R9_W), cdiv(l.h, R9_H), lanes);
-        KLAUNCH("riesz_analysis", i, k_riesz_analysis<<<grid, 256, 0, ctx.stream>>>(l, lv[(size_t)i + 1], oct[(size_t)i], cur_low[(size_t)i], oct[(size_t)i + 1]));
+        const int tma = ctx.use_tma && tm_valid[(size_t)i];
+        KLAUNCH("riesz_analysis", i, k_riesz_analysis<<<grid, 256, 0, ctx.stream>>>(l, lv[(size_t)i + 1], oct[(size_t)i], cur_low[(size_t)i], oct[(size_t)i + 1],
+                                                                                    *reinterpret_cast<const CUtensorMap*>(&tm_oct[(size_t)i]), tma));
     }
     return MC_OK;
 }
@@ -475,6 +501,13 @@ mc_status RieszMode::process(const ModeCtx& ctx, const FrameIO& io, const mc_par
         // init(): Riesz pair of `old`, phases and IIR registers start at zero (RieszPyramid.cpp:196-213, TemporalFilter.cpp:299-317)
         for (auto* v : {&old_rx, &old_ry, &phase_c, &phase_s, &lo_r0c, &lo_r0s, &lo_r1c, &lo_r1s, &hi_r0c, &hi_r0s, &hi_r1c, &hi_r1s})
             if ((st = alloc_set(*v, nb, true)) != MC_OK) return st;
+        // TMA descriptors for the tiles of the 9x9 kernels (option use_tma; tiles touching a border keep the reflected loads)
+        tm_oct.assign((size_t)levels, TensorMapStorage{});
+        tm_band.assign((size_t)levels, TensorMapStorage{});
+        tm_valid.assign((size_t)levels, 0);
+        for (int i = 0; i < nb; ++i)
+            tm_valid[(size_t)i] = make_tensor_map_box(&tm_oct[(size_t)i], oct[(size_t)i], lv[(size_t)i], lanes, R9_SW, R9_SH) &&
+                                  make_tensor_map_box(&tm_band[(size_t)i], low_amp[(size_t)i], lv[(size_t)i], lanes, R9_SW, R9_SH) ? 1 : 0;
         pitch16 = round_up(w, 64);
         plane16 = (size_t)h * pitch16;
         void* lp = nullptr;
@@ -572,7 +605,9 @@ mc_status RieszMode::process(const ModeCtx& ctx, const FrameIO& io, const mc_par
     for (int i = nb - 1; i >= 0; --i) {
         const Level& l = lv[(size_t)i];
         dim3 grid(cdiv(l.w, R9_W), cdiv(l.h, R9_H), lanes);
-        KLAUNCH("riesz_collapse", i, k_riesz_collapse<<<grid, 256, 0, ctx.stream>>>(l, lv[(size_t)i + 1], low_amp[(size_t)i], result, res[(size_t)i]));
+        const int tma = ctx.use_tma && tm_valid[(size_t)i];
+        KLAUNCH("riesz_collapse", i, k_riesz_collapse<<<grid, 256, 0, ctx.stream>>>(l, lv[(size_t)i + 1], low_amp[(size_t)i], result, res[(size_t)i],
+                                                                                    *reinterpret_cast<const CUtensorMap*>(&tm_band[(size_t)i]), tma));
         result = res[(size_t)i];
     }
     {

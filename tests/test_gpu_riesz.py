@@ -173,3 +173,23 @@ def test_flat_regions_nan_semantics_match_the_reference():
                 assert int(d.max()) <= 3 and float((d == 0).mean()) >= 0.995, (name, t, int(d.max()), float((d == 0).mean()))
                 if name == "letterbox":
                     assert (oout[:8] == 255).all() and (out[:8] == 255).all()      # the bars are white in both
+
+
+def test_tma_staged_riesz_tiles_equal_ldg_staging():
+    """The 9x9 analysis and collapse kernels stage their interior tiles with one cp.async.bulk.tensor copy each (option
+    use_tma, default on); use_tma = 0 selects 128-bit loads.  Bit-identical u8 frames and state planes, on a size with
+    interior and border tiles at several levels."""
+    w, h, levels = 400, 300, 4
+    cfg, _ = make_cfgs(O.MODE_PHASE, 40, 50.0, 0.4, 3.0, 0, levels, 30.0)
+    a, b = L.MagnificationProcessor(0), L.MagnificationProcessor(0)
+    b.set_option("use_tma", 0)
+    for t in range(5):
+        f = synth_frame(t, w, h, 3)
+        pa, oa = a.process_image(f, cfg)
+        pb, ob = b.process_image(f, cfg)
+        assert pa == pb
+        if pa:
+            assert np.array_equal(oa, ob), t
+    for lvl in range(levels - 1):
+        for name in ("old.lowpass", "old.rx", "phase.c", "lo.r0.c"):
+            assert np.array_equal(a.get_state(name, lvl), b.get_state(name, lvl)), (name, lvl)

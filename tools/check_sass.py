@@ -47,6 +47,8 @@ def main():
     need(bool(tma) and all(count(k, "UTMALDG") >= 1 and count(k, "SYNCS") >= 2 for k in tma), "k_level<f32, TMA, *>: cp.async.bulk.tensor (UTMALDG) + mbarrier (SYNCS)")
     pre = [k for k in tma if k.startswith("void k_level<0, true, true")]
     need(bool(pre) and all(count(k, "UTMALDG") == 3 for k in pre), "k_level<f32, TMA, PREFETCH>: three bulk-tensor copies (input window + both state tiles)")
+    r9 = [k for k in body if k.startswith("k_riesz_analysis(") or k.startswith("k_riesz_collapse(")]
+    need(len(r9) == 2 and all(count(k, "UTMALDG") == 1 and count(k, "SYNCS") >= 2 for k in r9), "k_riesz_analysis / k_riesz_collapse: 9x9 input tile by one bulk-tensor copy")
     ing = [k for k in body if k.startswith("void k_ingest_lab<")]
     need(bool(ing) and all(count(k, r"LDG\.E\.\S*256") >= 8 for k in ing), "k_ingest_lab: 256-bit LUT gathers (LDG.E.*.256)")
     strip = [k for k in body if k.startswith("void k_egress_strip<3")]
