@@ -35,12 +35,17 @@ log "5. other modes: device-resident fps + kernel tables; ncu --set full of the 
 for m in phase color laplace4k laplace_gray; do
     timeout 200 python tools/mode_bench.py $m >> gpurun_out/${tag}_other_modes.jsonl 2>> gpurun_out/${tag}_other_modes.err; log "   $m rc=$?"
 done
-timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_riesz -s 60 -c 14 -f -o gpurun_out/${tag}_full_riesz \
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_riesz -s 63 -c 21 -f -o gpurun_out/${tag}_full_riesz \
     python tools/mode_bench.py phase --steps 4 > gpurun_out/${tag}_ncu_riesz.log 2>&1; log "   riesz rc=$?"
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:'k_minmax|k_sum_minmax|k_pyrup2x|k_select|k_mask_mul' -s 300 -c 8 -f -o gpurun_out/${tag}_full_color \
     python tools/mode_bench.py color --steps 4 > gpurun_out/${tag}_ncu_color.log 2>&1; log "   color rc=$?"
 
-log "6. single-stream latency; hardware fuzz (2 min)"
+log "6. compute-sanitizer memcheck over the new kernels (strip egress, 256-bit LUT ingest, lane groups, TMA-staged Riesz tiles)"
+timeout 420 compute-sanitizer --tool memcheck --error-exitcode 1 python -m pytest tests/test_gpu_laplace.py tests/test_gpu_riesz.py -q -m gpu -p no:cacheprovider \
+    -k "strip_egress or lane_groups or ingest_warps or tma_staged or flat_regions or small" > gpurun_out/${tag}_compute_sanitizer.txt 2>&1; log "   rc=$?"
+tail -4 gpurun_out/${tag}_compute_sanitizer.txt
+
+log "7. single-stream latency; hardware fuzz (2 min)"
 timeout 200 python tools/latency.py > gpurun_out/${tag}_latency_lanes1.json 2> gpurun_out/${tag}_latency.err; log "   latency rc=$?"
 timeout 150 python tests/tools/fuzz_parity.py --cases 120 --seed 202 --max-size 400 --options > gpurun_out/${tag}_fuzz_gpu.log 2>&1; log "   fuzz rc=$?"
 log "done"
