@@ -1249,9 +1249,7 @@ cudaError_t launch_ingest_lab(const FrameIO& io, const DeviceTables& tb, int16_t
     a.aligned = (reinterpret_cast<uintptr_t>(io.in) % 4 == 0) && (io.in_step % 4 == 0) && (io.in_lane_stride % 4 == 0);
     a.lut = tb.lab_lut; a.lab = lab; a.pitch16 = pitch16; a.plane16 = plane16; a.g1 = g1; a.l1 = l1;
     if (warps != 2 && warps != 4) warps = 1;
-    // tall chunks halve the re-converted halo rows but measured slower at 64 lanes (29.9 k vs 30.7 k frames/s: fewer,
-    // longer CTAs balance worse): short is the default
-    const int rows = rows_per_warp == 64 ? 64 : 32;
+    const int rows = (rows_per_warp == 64 || (rows_per_warp == 0 && io.lanes >= 24)) ? 64 : 32;   // automatic: tall chunks once the grid stays > 2 waves
     dim3 grid(cdiv(io.w, DS_COLS), cdiv(l1.h, rows * warps), io.lanes);
     if (warps == 4) k_ingest_lab<4, 32><<<dim3(grid.x, cdiv(l1.h, 32 * 4), grid.z), 128, 0, s>>>(a);
     else if (warps == 2) k_ingest_lab<2, 32><<<dim3(grid.x, cdiv(l1.h, 32 * 2), grid.z), 64, 0, s>>>(a);
@@ -1313,7 +1311,7 @@ cudaError_t launch_egress(const FrameIO& io, const DeviceTables& tb, const int16
     a.gtab = tb.inv_gamma; a.coeffs = tb.inv_coeffs;
     a.m1 = m1; a.l1 = l1; a.c2 = c2; a.l2 = l2; a.chroma = chroma; a.fout = fout;
     if (strip) {
-        const bool tall = strip_rows == 128;
+        const bool tall = strip_rows == 128 || (strip_rows == 0 && io.lanes >= 24);
         dim3 grid(cdiv(io.w, DS_COLS), cdiv(io.h, tall ? 128 : 64), io.lanes);
         // the register cap (resident warps per SM) is an A/B knob: 16 -> <= 128 registers, 20 -> 96, 24 -> 80
         if (io.channels != 3) k_egress_strip<1, 24, 64><<<dim3(grid.x, cdiv(io.h, 64), grid.z), 32, 0, s>>>(a);
