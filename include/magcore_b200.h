@@ -171,9 +171,6 @@ void* mc_stream(mc_handle* h);
  *   "egress_strip" (default 20): Laplace egress runs as the shuffle strip kernel (one warp per 128-column strip,
  *        sliding windows in per-lane shared-memory rings; the value 16 / 20 / 24 picks the register cap = resident
  *        warps per SM); 0 selects the shared-memory tile kernel (bit-identical results; kept for A/B)
- *   "strip_rows" (default 0 = automatic: tall from 24 lanes per launch chain): rows a warp of the two strip kernels (ingest,
- *        egress) walks — 1 = 32 coarse / 64 output rows, 2 = 64 / 128 (halves the halo rows a chunk re-computes; needs enough
- *        lanes to keep the grid large; same results)
  *   "ingest_warps" (default 1): warps per CTA (1, 2 or 4) of the fused BGR->Lab ingest kernel (same results; A/B)
  *   "analysis_only" (default 0): Laplace and Phase — frames after the first update the temporal state (EMA planes;
  *        Riesz pyramids, phase accumulators and Butterworth registers) but skip synthesis and egress and report

@@ -50,7 +50,6 @@ struct mc_handle {
     int ingest_warps = 1;
     int egress_strip = 20;
     int lane_groups = 0;
-    int strip_rows = 0;
     Profiler prof;
     int depth = 3;
 
@@ -232,7 +231,7 @@ mc_status process_device_impl(mc_handle* h, const uint8_t* d_in, int w, int hh, 
         fout = h->float_out;
     }
 
-    ModeCtx ctx{h->stream, &h->tables, &h->launches, &h->err, h->faithful0, fout, h->profile ? &h->prof : nullptr, h->use_tma, h->prefetch_state, h->egress_strip, h->strip_rows, h->ingest_warps, h->band_from_state, h->profile ? 1 : h->lane_groups, h->analysis_only};
+    ModeCtx ctx{h->stream, &h->tables, &h->launches, &h->err, h->faithful0, fout, h->profile ? &h->prof : nullptr, h->use_tma, h->prefetch_state, h->egress_strip, h->ingest_warps, h->band_from_state, h->profile ? 1 : h->lane_groups, h->analysis_only};
     mc_status st = MC_OK;
     switch (p->mode) {
         case MC_MODE_LAPLACE: st = h->motion.process(ctx, io, *p, levels, produced); break;
@@ -423,7 +422,6 @@ mc_status mc_set_option(mc_handle* h, const char* key, int value) try {
     if (!std::strcmp(key, "profile_kernels")) { h->profile = value != 0; return MC_OK; }
     if (!std::strcmp(key, "use_tma")) { h->use_tma = value != 0; return MC_OK; }
     if (!std::strcmp(key, "prefetch_state")) { h->prefetch_state = value != 0; return MC_OK; }
-    if (!std::strcmp(key, "strip_rows")) { h->strip_rows = value; return MC_OK; }
     if (!std::strcmp(key, "lane_groups")) { h->lane_groups = value < 0 ? 0 : value; return MC_OK; }
     if (!std::strcmp(key, "egress_strip")) { h->egress_strip = value == 1 ? 20 : value; return MC_OK; }
     if (!std::strcmp(key, "ingest_warps")) { h->ingest_warps = value; return MC_OK; }

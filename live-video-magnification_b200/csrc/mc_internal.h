@@ -64,7 +64,7 @@ cudaError_t launch_lab16(const FrameIO& io, const DeviceTables& tb, int16_t* lab
 
 // fused ingest of the production path: u8 BGR -> Lab16 planes + G1 = pyrDown(Lab) (MagnifyCore.hpp:87-96, level 0)
 cudaError_t launch_ingest_lab(const FrameIO& io, const DeviceTables& tb, int16_t* lab, int pitch16, size_t plane16,
-                              float* g1, const Level& l1, cudaStream_t s, int warps_per_cta = 1, int rows_per_warp = 0);
+                              float* g1, const Level& l1, cudaStream_t s, int warps_per_cta = 1);
 
 struct LevelArgs {
     int in_kind = 0;           // 0: f32 planes, 1: Lab int16 planes, 2: u8 gray frame
@@ -113,7 +113,7 @@ cudaError_t launch_collapse(const Level& lf, const Level& lc, const BandSrc& fin
 // m1.a == nullptr: no motion; c2.a == nullptr: cur_1 = m1.  C == 3 reads `lab`, C == 1 reads io.in.
 cudaError_t launch_egress(const FrameIO& io, const DeviceTables& tb, const int16_t* lab, int pitch16, size_t plane16,
                           const BandSrc& m1, const Level& l1, const BandSrc& c2, const Level& l2, float chroma,
-                          float* float_out_or_null, cudaStream_t s, int strip = 20, int strip_rows = 0);
+                          float* float_out_or_null, cudaStream_t s, int strip = 20);
 
 // PreprocessProcessor + GrayscaleProcessor on the device (mc_preprocess.cu)
 cudaError_t launch_preprocess(const uint8_t* src_roi, size_t step, int cn, int sw, int sh, int dw, int dh, bool copy_only,

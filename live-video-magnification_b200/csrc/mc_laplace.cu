@@ -447,8 +447,7 @@ __global__ void __launch_bounds__(32 * DS_WARPS) k_down_strip(const DownArgs a) 
 // lookups) and by issue slots, not by HBM: each pixel costs two 256-bit gathers (LabLutCell) and ~80 instructions;
 // the next row's 12 input bytes per lane are requested before the current row is converted.
 // ------------------------------------------------------------------------------------------------
-// coarse rows per warp: 32 (halo rows re-convert 4 of 68 fine rows) or, when there are enough streams to keep the
-// grid large, 64 (4 of 132)
+constexpr int IG_ROWS = 32;   // coarse rows per warp (halo rows re-convert 4 of 68 fine rows)
 
 struct IngestArgs {
     const uint8_t* in; size_t in_step, in_lane_stride;
@@ -513,7 +512,7 @@ __device__ __forceinline__ void ig_row(const IngestArgs& a, const IgRaw raw, int
     o = ds_rowpass(r); hB[0] = o.h0; hB[1] = o.h1;
 }
 
-template <int WARPS, int IG_ROWS>
+template <int WARPS>
 __global__ void __launch_bounds__(32 * WARPS) k_ingest_lab(const IngestArgs a) {
     const int lane_id = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int lane = blockIdx.z;                                       // stream
@@ -921,12 +920,12 @@ __device__ __forceinline__ EgressIn<1> egress_row1<1>(const uint8_t* row, int gx
 template <>
 __device__ __forceinline__ EgressIn<3> egress_row1<3>(const uint8_t*, int, int) { return EgressIn<3>{}; }
 
-// output rows per warp (a multiple of 4): 64, or 128 when there are enough streams to keep the grid large
+constexpr int EG_ROWS = 64;   // output rows per warp (a multiple of 4)
 
 template <int C> struct StripM1 { float2 h[C], l[C]; };   // band-1 source of one cur_1 row at the lane's two columns
 template <int C> struct StripH2 { float v[C], vb[C], vr[C], vrb[C]; };   // one level-2 row at the lane's column (+ lane 31's right neighbour); b: lo state
 
-template <int C, int MINB, int EG_ROWS>
+template <int C, int MINB>
 __global__ void __launch_bounds__(32, MINB) k_egress_strip(const EgressArgs a) {
     const unsigned full = 0xffffffffu;
     const int lane_id = threadIdx.x;
@@ -1242,19 +1241,17 @@ cudaError_t launch_lab16(const FrameIO& io, const DeviceTables& tb, int16_t* lab
 }
 
 cudaError_t launch_ingest_lab(const FrameIO& io, const DeviceTables& tb, int16_t* lab, int pitch16, size_t plane16,
-                              float* g1, const Level& l1, cudaStream_t s, int warps, int rows_per_warp) {
+                              float* g1, const Level& l1, cudaStream_t s, int warps) {
     IngestArgs a;
     a.in = io.in; a.in_step = io.in_step; a.in_lane_stride = io.in_lane_stride;
     a.w = io.w; a.h = io.h;
     a.aligned = (reinterpret_cast<uintptr_t>(io.in) % 4 == 0) && (io.in_step % 4 == 0) && (io.in_lane_stride % 4 == 0);
     a.lut = tb.lab_lut; a.lab = lab; a.pitch16 = pitch16; a.plane16 = plane16; a.g1 = g1; a.l1 = l1;
     if (warps != 2 && warps != 4) warps = 1;
-    const int rows = (rows_per_warp == 64 || (rows_per_warp == 0 && io.lanes >= 24)) ? 64 : 32;   // automatic: tall chunks once the grid stays > 2 waves
-    dim3 grid(cdiv(io.w, DS_COLS), cdiv(l1.h, rows * warps), io.lanes);
-    if (warps == 4) k_ingest_lab<4, 32><<<dim3(grid.x, cdiv(l1.h, 32 * 4), grid.z), 128, 0, s>>>(a);
-    else if (warps == 2) k_ingest_lab<2, 32><<<dim3(grid.x, cdiv(l1.h, 32 * 2), grid.z), 64, 0, s>>>(a);
-    else if (rows == 64) k_ingest_lab<1, 64><<<grid, 32, 0, s>>>(a);
-    else k_ingest_lab<1, 32><<<grid, 32, 0, s>>>(a);
+    dim3 grid(cdiv(io.w, DS_COLS), cdiv(l1.h, IG_ROWS * warps), io.lanes);
+    if (warps == 4) k_ingest_lab<4><<<grid, 128, 0, s>>>(a);
+    else if (warps == 2) k_ingest_lab<2><<<grid, 64, 0, s>>>(a);
+    else k_ingest_lab<1><<<grid, 32, 0, s>>>(a);
     return cudaGetLastError();
 }
 
@@ -1302,7 +1299,7 @@ cudaError_t launch_collapse(const Level& lf, const Level& lc, const BandSrc& fin
 
 cudaError_t launch_egress(const FrameIO& io, const DeviceTables& tb, const int16_t* lab, int pitch16, size_t plane16,
                           const BandSrc& m1, const Level& l1, const BandSrc& c2, const Level& l2, float chroma,
-                          float* fout, cudaStream_t s, int strip, int strip_rows) {
+                          float* fout, cudaStream_t s, int strip) {
     EgressArgs a;
     a.in = io.in; a.in_step = io.in_step; a.in_lane_stride = io.in_lane_stride;
     a.lab = lab; a.pitch16 = pitch16; a.plane16 = plane16;
@@ -1311,14 +1308,12 @@ cudaError_t launch_egress(const FrameIO& io, const DeviceTables& tb, const int16
     a.gtab = tb.inv_gamma; a.coeffs = tb.inv_coeffs;
     a.m1 = m1; a.l1 = l1; a.c2 = c2; a.l2 = l2; a.chroma = chroma; a.fout = fout;
     if (strip) {
-        const bool tall = strip_rows == 128 || (strip_rows == 0 && io.lanes >= 24);
-        dim3 grid(cdiv(io.w, DS_COLS), cdiv(io.h, tall ? 128 : 64), io.lanes);
+        dim3 grid(cdiv(io.w, DS_COLS), cdiv(io.h, EG_ROWS), io.lanes);
         // the register cap (resident warps per SM) is an A/B knob: 16 -> <= 128 registers, 20 -> 96, 24 -> 80
-        if (io.channels != 3) k_egress_strip<1, 24, 64><<<dim3(grid.x, cdiv(io.h, 64), grid.z), 32, 0, s>>>(a);
-        else if (strip == 16) k_egress_strip<3, 16, 64><<<dim3(grid.x, cdiv(io.h, 64), grid.z), 32, 0, s>>>(a);
-        else if (strip == 24) k_egress_strip<3, 24, 64><<<dim3(grid.x, cdiv(io.h, 64), grid.z), 32, 0, s>>>(a);
-        else if (tall) k_egress_strip<3, 20, 128><<<grid, 32, 0, s>>>(a);
-        else k_egress_strip<3, 20, 64><<<grid, 32, 0, s>>>(a);
+        if (io.channels != 3) k_egress_strip<1, 24><<<grid, 32, 0, s>>>(a);
+        else if (strip == 16) k_egress_strip<3, 16><<<grid, 32, 0, s>>>(a);
+        else if (strip == 24) k_egress_strip<3, 24><<<grid, 32, 0, s>>>(a);
+        else k_egress_strip<3, 20><<<grid, 32, 0, s>>>(a);
     } else {
         dim3 grid(cdiv(io.w, TW), cdiv(io.h, TH), io.lanes);
         if (io.channels == 3) k_egress<3><<<grid, 256, 0, s>>>(a);

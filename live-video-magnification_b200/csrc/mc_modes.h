@@ -40,7 +40,6 @@ struct ModeCtx {
                             // B200, 32 lanes: level[1] 235 -> 205 us)
     int egress_strip;       // Laplace egress as the register/shuffle strip kernel (option "egress_strip": 0 = tile kernel,
                             // 16 / 20 / 24 = strip kernel compiled for that many resident warps per SM)
-    int strip_rows;         // rows per warp of the two strip kernels (option "strip_rows": 0 = automatic, 1 = short (32 coarse / 64 output rows), 2 = tall)
     int ingest_warps;       // warps per CTA of the fused ingest kernel (option "ingest_warps": 1, 2 or 4)
     bool band_from_state;   // synthesis rebuilds gain*(hi-lo) from the state planes instead of reading a stored band
                             // (option "band_from_state", default on: with prefetch_state level[1] 205 -> 177 us, egress +8 us)

@@ -184,7 +184,7 @@ mc_status MotionMode::run_group(const ModeCtx& ctx, const FrameIO& io_all, const
     // ingest: u8 BGR -> Lab16 planes (gray frames are read directly by the level-0 kernel)
     // (production path, >= 2 levels: one fused kernel also builds G1; otherwise Lab16 alone)
     const bool fused_ingest = channels == 3 && !faithful && levels >= 2;
-    if (fused_ingest) LAUNCH("ingest_lab", 0, launch_ingest_lab(io, *ctx.tables, lab, pitch16, plane16, off(G[1], 1), lv[1], ctx.stream, ctx.ingest_warps, ctx.strip_rows == 1 ? 32 : (ctx.strip_rows == 2 ? 64 : 0)));
+    if (fused_ingest) LAUNCH("ingest_lab", 0, launch_ingest_lab(io, *ctx.tables, lab, pitch16, plane16, off(G[1], 1), lv[1], ctx.stream, ctx.ingest_warps));
     else if (channels == 3) LAUNCH("lab16", 0, launch_lab16(io, *ctx.tables, lab, pitch16, plane16, ctx.stream));
 
     // analysis: one fused kernel per level (level 0 only builds G1 unless the faithful option is on)
@@ -243,7 +243,7 @@ mc_status MotionMode::run_group(const ModeCtx& ctx, const FrameIO& io_all, const
     const Level& l1 = lv[levels >= 1 ? 1 : 0];
     const Level& l2 = lv[levels >= 2 ? 2 : 0];
     LAUNCH("egress", 0, launch_egress(io, *ctx.tables, lab, pitch16, plane16, m1, l1, c2, l2, (float)p.chromAttenuation, fout,
-                                      ctx.stream, ctx.egress_strip, ctx.strip_rows == 1 ? 64 : (ctx.strip_rows == 2 ? 128 : 0)));
+                                      ctx.stream, ctx.egress_strip));
     return MC_OK;
 }
 

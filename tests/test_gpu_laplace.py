@@ -349,7 +349,7 @@ def test_prefetch_state_option_equals_default():
 
 @pytest.mark.parametrize("opts", [{"prefetch_state": 0}, {"band_from_state": 0}, {"prefetch_state": 0, "band_from_state": 0},
                                   {"use_tma": 0}, {"ingest_warps": 2, "band_from_state": 0}, {"ingest_warps": 4},
-                                  {"egress_strip": 0}, {"egress_strip": 0, "band_from_state": 0}, {"strip_rows": 2}, {"strip_rows": 1}])
+                                  {"egress_strip": 0}, {"egress_strip": 0, "band_from_state": 0}])
 def test_option_combinations_agree_with_default(opts):
     """The A/B options compose: any combination gives the default path's frames bit for bit, over the first frame,
     ragged borders and a parameter change."""
