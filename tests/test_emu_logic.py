@@ -153,3 +153,44 @@ def test_color_many_lanes_and_frame_rate_sweep(emu):
                 assert int(u8_diff(out, oout).max()) <= 1, (fps, t)
             t += 1
     proc.close()
+
+
+def test_round2_kernel_forms_agree_on_emulation(emu):
+    """Round-2 kernel forms, logic only (the B200 runs the same checks in test_gpu_laplace.py / test_gpu_riesz.py):
+    (1) the shuffle-strip egress equals the shared-memory tile egress bit for bit over several strips and chunks, both band
+    sources, float taps included; (2) lanes run as two launch chains (option lane_groups) equal one chain; (3) the 9x9 Riesz
+    kernels give the same bits with TMA-staged and with LDG-staged tiles."""
+    w, h, lv = 250, 131, 3
+    cfg, _ = make_cfgs(O.MODE_LAPLACE, 20, 50.0, 0.4, 3.0, 30, lv)
+    for bfs in (1, 0):
+        a, b = L.MagnificationProcessor(0), L.MagnificationProcessor(0)
+        for p in (a, b):
+            p.set_option("band_from_state", bfs)
+            p.set_option("keep_float_output", 1)
+        b.set_option("egress_strip", 0)
+        for t in range(3):
+            f = synth_frame(t, w, h, 3)
+            _, oa = a.process_image(f, cfg)
+            _, ob = b.process_image(f, cfg)
+            assert np.array_equal(oa, ob), (bfs, t)
+            assert np.array_equal(a.float_output(w, h, 3), b.float_output(w, h, 3)), (bfs, t)
+        a.close(); b.close()
+    lanes = 5
+    a, b = L.MagnificationProcessor(0, lanes=lanes), L.MagnificationProcessor(0, lanes=lanes)
+    a.set_option("lane_groups", 1)
+    b.set_option("lane_groups", 2)
+    for t in range(3):
+        f = np.stack([np.roll(synth_frame(t, 130, 70, 3), (3 * k, 7 * k), axis=(0, 1)) for k in range(lanes)])
+        _, oa = a.process_image(f, cfg)
+        _, ob = b.process_image(f, cfg)
+        assert np.array_equal(oa, ob), t
+    a.close(); b.close()
+    cfgp, _ = make_cfgs(O.MODE_PHASE, 40, 50.0, 0.4, 3.0, 0, 3, 30.0)
+    a, b = L.MagnificationProcessor(0), L.MagnificationProcessor(0)
+    b.set_option("use_tma", 0)
+    for t in range(3):
+        f = synth_frame(t, 230, 120, 3)
+        pa, oa = a.process_image(f, cfgp)
+        pb, ob = b.process_image(f, cfgp)
+        assert pa == pb and (not pa or np.array_equal(oa, ob)), t
+    a.close(); b.close()
