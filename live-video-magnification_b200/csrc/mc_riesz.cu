@@ -52,6 +52,15 @@ __device__ __forceinline__ float mulr(float a, float b) { return __fmul_rn(a, b)
 __device__ __forceinline__ float addr(float a, float b) { return __fadd_rn(a, b); }
 __device__ __forceinline__ float subr(float a, float b) { return __fsub_rn(a, b); }
 
+// cv::filter2D's f32 engine (FilterVec_32f + scalar remainder; OpenCV 4.x, the AVX2 dispatch both this container and the
+// B200 boxes run, tools/probe_filter2d_order.py): every output accumulates its non-zero taps in raster order — with one
+// FMA per tap in the vectorised columns x < (w & ~7), with multiply-then-add in the scalar tail columns.  The device
+// kernels follow that rule column by column, which makes the band planes and the Riesz pair bit-identical to the
+// reference for every width (acos near 1 turns a last-ulp difference here into visible differences downstream).
+__device__ __forceinline__ float f2d(float c, float v, float acc, bool tail) {
+    return tail ? __fadd_rn(acc, __fmul_rn(c, v)) : fmaf(c, v, acc);
+}
+
 // 9x9 kernels are register-blocked: a thread owns a 1x4 strip, loads 12 tile values per kernel row with three
 // 128-bit shared-memory reads and issues 36 FMAs on them.  Rows are dealt to warps so that both rows of a
 // warp have the same parity (the sub-sampled low-pass / the zero-injected up-sampling only touch one parity),
@@ -110,24 +119,49 @@ __global__ void __launch_bounds__(256) k_riesz_analysis(Level l, Level ln, const
     if (gy >= l.h || gx >= l.w) return;
     float acc[4] = {0.f, 0.f, 0.f, 0.f}, lp0 = 0.f, lp1 = 0.f;
     const bool even_row = next != nullptr && !(gy & 1);   // warp-uniform
+    const int tail_from = (l.w & ~7) - gx;                 // strip columns p >= tail_from are filter2D's scalar-tail columns
+    if (tail_from >= 4) {
 #pragma unroll
-    for (int ky = 0; ky < 9; ++ky) {
-        const float4 a0 = *reinterpret_cast<const float4*>(&s[y + ky][4 * tx]);
-        const float4 a1 = *reinterpret_cast<const float4*>(&s[y + ky][4 * tx + 4]);
-        const float4 a2 = *reinterpret_cast<const float4*>(&s[y + ky][4 * tx + 8]);
-        const float v[12] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x, a2.y, a2.z, a2.w};
-#pragma unroll
-        for (int kx = 0; kx < 9; ++kx) {
-            const float c = c_hp[ky * 9 + kx];
-#pragma unroll
-            for (int p = 0; p < 4; ++p) acc[p] = fmaf(c, v[p + kx], acc[p]);
-        }
-        if (even_row) {
+        for (int ky = 0; ky < 9; ++ky) {
+            const float4 a0 = *reinterpret_cast<const float4*>(&s[y + ky][4 * tx]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&s[y + ky][4 * tx + 4]);
+            const float4 a2 = *reinterpret_cast<const float4*>(&s[y + ky][4 * tx + 8]);
+            const float v[12] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x, a2.y, a2.z, a2.w};
 #pragma unroll
             for (int kx = 0; kx < 9; ++kx) {
-                const float c = 2.0f * c_lp[ky * 9 + kx];
-                lp0 = fmaf(c, v[kx], lp0);
-                lp1 = fmaf(c, v[2 + kx], lp1);
+                const float c = c_hp[ky * 9 + kx];
+#pragma unroll
+                for (int p = 0; p < 4; ++p) acc[p] = fmaf(c, v[p + kx], acc[p]);
+            }
+            if (even_row) {
+#pragma unroll
+                for (int kx = 0; kx < 9; ++kx) {
+                    const float c = 2.0f * c_lp[ky * 9 + kx];
+                    lp0 = fmaf(c, v[kx], lp0);
+                    lp1 = fmaf(c, v[2 + kx], lp1);
+                }
+            }
+        }
+    } else {   // the last strip(s) of a row whose width is not a multiple of 8
+#pragma unroll
+        for (int ky = 0; ky < 9; ++ky) {
+            const float4 a0 = *reinterpret_cast<const float4*>(&s[y + ky][4 * tx]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&s[y + ky][4 * tx + 4]);
+            const float4 a2 = *reinterpret_cast<const float4*>(&s[y + ky][4 * tx + 8]);
+            const float v[12] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x, a2.y, a2.z, a2.w};
+#pragma unroll
+            for (int kx = 0; kx < 9; ++kx) {
+                const float c = c_hp[ky * 9 + kx];
+#pragma unroll
+                for (int p = 0; p < 4; ++p) acc[p] = f2d(c, v[p + kx], acc[p], p >= tail_from);
+            }
+            if (even_row) {
+#pragma unroll
+                for (int kx = 0; kx < 9; ++kx) {
+                    const float c = 2.0f * c_lp[ky * 9 + kx];
+                    lp0 = f2d(c, v[kx], lp0, 0 >= tail_from);
+                    lp1 = f2d(c, v[2 + kx], lp1, 2 >= tail_from);
+                }
             }
         }
     }
@@ -180,14 +214,15 @@ __global__ void __launch_bounds__(256) k_riesz_phase(const PhaseArgs a) {
         const size_t o = pb + (size_t)gy * l.pitch + gx;
         // RieszPyramidLevel::build (RieszPyramid.cpp:66-78): taps [-0.2, -0.48, 0, 0.48, 0.2]
         const float low = s[y + 2][x + 2];
-        float rx = -0.2f * s[y + 2][x];
-        rx = fmaf(-0.48f, s[y + 2][x + 1], rx);
-        rx = fmaf(0.48f, s[y + 2][x + 3], rx);
-        rx = fmaf(0.2f, s[y + 2][x + 4], rx);
-        float ry = -0.2f * s[y][x + 2];
-        ry = fmaf(-0.48f, s[y + 1][x + 2], ry);
-        ry = fmaf(0.48f, s[y + 3][x + 2], ry);
-        ry = fmaf(0.2f, s[y + 4][x + 2], ry);
+        const bool tail = gx >= (l.w & ~7);     // filter2D's scalar-tail columns, see f2d()
+        float rx = mulr(-0.2f, s[y + 2][x]);
+        rx = f2d(-0.48f, s[y + 2][x + 1], rx, tail);
+        rx = f2d(0.48f, s[y + 2][x + 3], rx, tail);
+        rx = f2d(0.2f, s[y + 2][x + 4], rx, tail);
+        float ry = mulr(-0.2f, s[y][x + 2]);
+        ry = f2d(-0.48f, s[y + 1][x + 2], ry, tail);
+        ry = f2d(0.48f, s[y + 3][x + 2], ry, tail);
+        ry = f2d(0.2f, s[y + 4][x + 2], ry, tail);
         a.rx[o] = rx;
         a.ry[o] = ry;
         const float plow = a.plow ? a.plow[o] : low;
@@ -343,8 +378,8 @@ __global__ void __launch_bounds__(256) k_riesz_amplify(const AmpArgs a) {
 // evaluated (25/20/20/16 of 81, by output parity), reading the coarse samples straight from shared memory.
 constexpr int RC_CW = R9_SW / 2, RC_CH = R9_SH / 2;   // even fine positions of the window: 36 x 12
 
-template <int PAR>   // PAR = parity of the output row
-__device__ __forceinline__ void rc_lowpass(const float (*sc)[RC_CW], int y, int tx, float (&lp)[4]) {
+template <int PAR, bool MIXED>   // PAR = parity of the output row; MIXED: some of the strip's columns are filter2D tail columns
+__device__ __forceinline__ void rc_lowpass(const float (*sc)[RC_CW], int y, int tx, int tail_from, float (&lp)[4]) {
     // output (y, x): taps ky = PAR, PAR+2, ... on coarse row (y + ky) / 2 ; kx likewise by column parity
 #pragma unroll
     for (int i = 0; i < 5 - PAR; ++i) {
@@ -357,14 +392,14 @@ __device__ __forceinline__ void rc_lowpass(const float (*sc)[RC_CW], int y, int 
 #pragma unroll
         for (int j = 0; j < 5; ++j) {                               // even outputs x, x+2: kx = 0,2,4,6,8
             const float c = 2.0f * c_lp[ky * 9 + 2 * j];
-            lp[0] = fmaf(c, v[j], lp[0]);
-            lp[2] = fmaf(c, v[j + 1], lp[2]);
+            lp[0] = MIXED ? f2d(c, v[j], lp[0], 0 >= tail_from) : fmaf(c, v[j], lp[0]);
+            lp[2] = MIXED ? f2d(c, v[j + 1], lp[2], 2 >= tail_from) : fmaf(c, v[j + 1], lp[2]);
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {                               // odd outputs x+1, x+3: kx = 1,3,5,7
             const float c = 2.0f * c_lp[ky * 9 + 2 * j + 1];
-            lp[1] = fmaf(c, v[j + 1], lp[1]);
-            lp[3] = fmaf(c, v[j + 2], lp[3]);
+            lp[1] = MIXED ? f2d(c, v[j + 1], lp[1], 1 >= tail_from) : fmaf(c, v[j + 1], lp[1]);
+            lp[3] = MIXED ? f2d(c, v[j + 2], lp[3], 3 >= tail_from) : fmaf(c, v[j + 2], lp[3]);
         }
     }
 }
@@ -394,21 +429,37 @@ __global__ void __launch_bounds__(256) k_riesz_collapse(Level l, Level lc, const
     const int gy = y0 + y, gx = x0 + 4 * tx;
     if (gy >= l.h || gx >= l.w) return;
     float hp[4] = {0.f, 0.f, 0.f, 0.f}, lp[4] = {0.f, 0.f, 0.f, 0.f};
+    const int tail_from = (l.w & ~7) - gx;                 // see f2d(): both filter2D calls run at this level's width
+    const bool mixed = tail_from < 4;
 #pragma unroll
     for (int ky = 0; ky < 9; ++ky) {
         const float4 a0 = *reinterpret_cast<const float4*>(&sb[y + ky][4 * tx]);
         const float4 a1 = *reinterpret_cast<const float4*>(&sb[y + ky][4 * tx + 4]);
         const float4 a2 = *reinterpret_cast<const float4*>(&sb[y + ky][4 * tx + 8]);
         const float v[12] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x, a2.y, a2.z, a2.w};
+        if (!mixed) {
 #pragma unroll
-        for (int kx = 0; kx < 9; ++kx) {
-            const float cf = c_hp[ky * 9 + kx];
+            for (int kx = 0; kx < 9; ++kx) {
+                const float cf = c_hp[ky * 9 + kx];
 #pragma unroll
-            for (int p = 0; p < 4; ++p) hp[p] = fmaf(cf, v[p + kx], hp[p]);
+                for (int p = 0; p < 4; ++p) hp[p] = fmaf(cf, v[p + kx], hp[p]);
+            }
+        } else {
+#pragma unroll
+            for (int kx = 0; kx < 9; ++kx) {
+                const float cf = c_hp[ky * 9 + kx];
+#pragma unroll
+                for (int p = 0; p < 4; ++p) hp[p] = f2d(cf, v[p + kx], hp[p], p >= tail_from);
+            }
         }
     }
-    if (y & 1) rc_lowpass<1>(sc, y, tx, lp);   // warp-uniform (r9_row)
-    else rc_lowpass<0>(sc, y, tx, lp);
+    if (!mixed) {
+        if (y & 1) rc_lowpass<1, false>(sc, y, tx, tail_from, lp);   // warp-uniform (r9_row)
+        else rc_lowpass<0, false>(sc, y, tx, tail_from, lp);
+    } else {
+        if (y & 1) rc_lowpass<1, true>(sc, y, tx, tail_from, lp);
+        else rc_lowpass<0, true>(sc, y, tx, tail_from, lp);
+    }
     float* o = out + (size_t)plane * l.plane + (size_t)gy * l.pitch + gx;
     *reinterpret_cast<float4*>(o) = make_float4(addr(lp[0], hp[0]), addr(lp[1], hp[1]), addr(lp[2], hp[2]), addr(lp[3], hp[3]));
 }

@@ -194,3 +194,21 @@ def test_round2_kernel_forms_agree_on_emulation(emu):
         pb, ob = b.process_image(f, cfgp)
         assert pa == pb and (not pa or np.array_equal(oa, ob)), t
     a.close(); b.close()
+
+
+def test_riesz_band_planes_bit_identical_on_odd_widths_on_emulation(emu):
+    """mc_riesz.cu::f2d — cv::filter2D's FMA / multiply-then-add column rule: band planes and Riesz pair equal the
+    oracle's bit for bit on a width that is not a multiple of 8 (the B200 runs the same check in test_gpu_riesz.py)."""
+    w, h, levels = 71, 76, 4
+    cfg, ocfg = make_cfgs(O.MODE_PHASE, 50, 50.0, 0.4, 3.0, 0, levels, 30.0)
+    proc, op = L.MagnificationProcessor(0), O.MagnificationProcessor()
+    for t in range(3):
+        f = synth_frame(t, w, h, 3)
+        _, out = proc.process_image(f, cfg)
+        _, oout = op.process(f, ocfg)
+    assert np.array_equal(out, oout)                       # libm on both sides: the whole frame is identical here
+    for lvl in range(levels - 1):
+        ref = op.riesz.old.levels[lvl]
+        for name, plane in (("old.lowpass", ref.lowpass), ("old.rx", ref.rx), ("old.ry", ref.ry)):
+            assert np.array_equal(proc.get_state(name, lvl)[0, 0], np.asarray(plane)), (name, lvl)
+    proc.close()
