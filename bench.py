@@ -412,8 +412,6 @@ def run_ours(args, rank, world, local_rank):
     clocks = sampler.stop() if rank == 0 else None
     e2e_fps = world * lanes * args.steps / e2e_s
     barrier()
-    if prev_affinity is not None:
-        os.sched_setaffinity(0, prev_affinity)   # the CPU baseline below uses every host core again
 
     # ---- the call the drop-in adapter makes: ONE stream, blocking mc_process, host frame in / host frame out ----
     single = None
@@ -438,9 +436,13 @@ def run_ours(args, rank, world, local_rank):
             sp.collect()                                           # pinned (mc_host_alloc-style) frames
             lat_pin.append(time.perf_counter() - t0)
         sp.close()
+        # (still bound to the GPU's NUMA node: the pinned frames above were first-touched next to the GPU's PCIe root)
         single = {"lanes": 1, "pageable_ms_median": statistics.median(lat_pg) * 1e3, "pinned_ms_median": statistics.median(lat_pin) * 1e3,
                   "pageable_fps": 1.0 / statistics.median(lat_pg), "pinned_fps": 1.0 / statistics.median(lat_pin),
                   "note": "blocking call per frame, copies included; what MagnificationProcessorB200::process does per cv::Mat"}
+
+    if prev_affinity is not None:
+        os.sched_setaffinity(0, prev_affinity)   # the CPU baseline below uses every host core again
 
     # ---- per-kernel device time (roofline of the dominant kernel) -------------------------------
     roof = None
