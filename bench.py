@@ -432,8 +432,7 @@ def run_ours(args, rank, world, local_rank):
             lat_pg.append(time.perf_counter() - t0)
         for i in range(40):
             t0 = time.perf_counter()
-            sp.submit(pin_in[i % 4].data_ptr(), W, H, CH, row, p, pin_out.data_ptr(), row)
-            sp.collect()                                           # pinned (mc_host_alloc-style) frames
+            sp.process_host(pin_in[i % 4].data_ptr(), W, H, CH, row, p, pin_out.data_ptr(), row)   # pinned (mc_host_alloc-style) frames
             lat_pin.append(time.perf_counter() - t0)
         sp.close()
         # (still bound to the GPU's NUMA node: the pinned frames above were first-touched next to the GPU's PCIe root)

@@ -206,6 +206,14 @@ class MagnificationProcessor(IProcessor):
                                                 C.byref(produced)))
         return bool(produced.value)
 
+    def process_host(self, in_ptr: int, w: int, h: int, c: int, in_step: int, cfg_or_params, out_ptr: int, out_step: int) -> bool:
+        """The blocking C call (mc_process) on raw host pointers — what the C++ adapter does per cv::Mat; with page-locked
+        buffers (mc_host_alloc, torch pin_memory) the copies go straight to / from HBM."""
+        p = cfg_or_params if isinstance(cfg_or_params, McParams) else _to_mc(cfg_or_params)
+        produced = C.c_int(0)
+        self._check(self._lib.mc_process(self._h, in_ptr, w, h, c, in_step, C.byref(p), out_ptr, out_step, C.byref(produced)))
+        return bool(produced.value)
+
     def submit(self, in_ptr: int, w: int, h: int, c: int, in_step: int, cfg_or_params, out_ptr: int, out_step: int):
         p = cfg_or_params if isinstance(cfg_or_params, McParams) else _to_mc(cfg_or_params)
         self._check(self._lib.mc_submit(self._h, in_ptr, w, h, c, in_step, C.byref(p), out_ptr, out_step))

@@ -37,8 +37,7 @@ def main():
         lat_p = []
         for i in range(40):
             t0 = time.perf_counter()
-            proc.submit(pin_in[i % 4].data_ptr(), W, H, 3, W * 3, p, pin_out.data_ptr(), W * 3)
-            proc.collect()
+            proc.process_host(pin_in[i % 4].data_ptr(), W, H, 3, W * 3, p, pin_out.data_ptr(), W * 3)   # blocking mc_process
             lat_p.append(time.perf_counter() - t0)
         out[mode] = {"pageable_ms_median": float(np.median(lat) * 1e3), "pinned_ms_median": float(np.median(lat_p) * 1e3)}
     print(json.dumps(out))
