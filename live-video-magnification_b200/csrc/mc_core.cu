@@ -459,12 +459,9 @@ mc_status mc_process_device(mc_handle* h, const uint8_t* d_in, int width, int he
 
 // submit with the destination known up front: when `in`/`out` are pinned (cudaHostAlloc /
 // cudaHostRegister) the copies go straight between the caller's buffers and HBM (no staging memcpy).
-// `serial`: the blocking call (mc_process) has a single frame in flight, so upload, kernels and download go onto the
-// handle's stream back to back — no cross-stream event hops, which only cost latency when nothing overlaps.
-static mc_status submit_impl(mc_handle* h, const uint8_t* in, int width, int height, int channels, size_t in_step,
-                             const mc_params* p, uint8_t* out, size_t out_step, bool serial) {
+mc_status mc_submit(mc_handle* h, const uint8_t* in, int width, int height, int channels, size_t in_step,
+                    const mc_params* p, uint8_t* out, size_t out_step) try {
     if (!h || !p) return MC_ERR_INVALID;
-    cudaStream_t s_in = serial ? h->stream : h->s_in, s_out = serial ? h->stream : h->s_out;
     CK(cudaSetDevice(h->device));
     if ((int)h->inflight.size() >= h->depth) { h->err = "pipeline full: call mc_collect first"; return MC_ERR_INVALID; }
     const bool have = in != nullptr && width > 0 && height > 0 && (channels == 1 || channels == 3);
@@ -489,31 +486,29 @@ static mc_status submit_impl(mc_handle* h, const uint8_t* in, int width, int hei
     }
     const size_t rows = (size_t)height * h->lanes;
     if (is_pinned(in)) {
-        if (in_step == row) CK(cudaMemcpyAsync(s.d_in, in, bytes, cudaMemcpyHostToDevice, s_in));
-        else CK(cudaMemcpy2DAsync(s.d_in, row, in, in_step, row, rows, cudaMemcpyHostToDevice, s_in));
+        if (in_step == row) CK(cudaMemcpyAsync(s.d_in, in, bytes, cudaMemcpyHostToDevice, h->s_in));
+        else CK(cudaMemcpy2DAsync(s.d_in, row, in, in_step, row, rows, cudaMemcpyHostToDevice, h->s_in));
     } else {
         for (size_t r = 0; r < rows; ++r) std::memcpy(s.h_in + r * row, in + r * in_step, row);
-        CK(cudaMemcpyAsync(s.d_in, s.h_in, bytes, cudaMemcpyHostToDevice, s_in));
+        CK(cudaMemcpyAsync(s.d_in, s.h_in, bytes, cudaMemcpyHostToDevice, h->s_in));
     }
-    if (!serial) {
-        CK(cudaEventRecord(s.ev_in, s_in));
-        CK(cudaStreamWaitEvent(h->stream, s.ev_in, 0));
-    }
+    CK(cudaEventRecord(s.ev_in, h->s_in));
+    CK(cudaStreamWaitEvent(h->stream, s.ev_in, 0));
     int produced = 0;
     st = process_device_impl(h, s.d_in, width, height, channels, row, p, s.d_out, row, &produced);
     if (st != MC_OK) return st;
     s.produced = produced;
-    if (!serial) CK(cudaEventRecord(s.ev_k, h->stream));
+    CK(cudaEventRecord(s.ev_k, h->stream));
     if (produced) {
-        if (!serial) CK(cudaStreamWaitEvent(s_out, s.ev_k, 0));
+        CK(cudaStreamWaitEvent(h->s_out, s.ev_k, 0));
         if (out && is_pinned(out)) {
-            if (out_step == row) CK(cudaMemcpyAsync(out, s.d_out, bytes, cudaMemcpyDeviceToHost, s_out));
-            else CK(cudaMemcpy2DAsync(out, out_step, s.d_out, row, row, rows, cudaMemcpyDeviceToHost, s_out));
+            if (out_step == row) CK(cudaMemcpyAsync(out, s.d_out, bytes, cudaMemcpyDeviceToHost, h->s_out));
+            else CK(cudaMemcpy2DAsync(out, out_step, s.d_out, row, row, rows, cudaMemcpyDeviceToHost, h->s_out));
             s.direct_out = true;
         } else if (out) {
-            CK(cudaMemcpyAsync(s.h_out, s.d_out, bytes, cudaMemcpyDeviceToHost, s_out));
+            CK(cudaMemcpyAsync(s.h_out, s.d_out, bytes, cudaMemcpyDeviceToHost, h->s_out));
         }
-        CK(cudaEventRecord(s.ev_done, s_out));
+        CK(cudaEventRecord(s.ev_done, h->s_out));
     } else {
         CK(cudaEventRecord(s.ev_done, h->stream));
     }
@@ -522,11 +517,6 @@ static mc_status submit_impl(mc_handle* h, const uint8_t* in, int width, int hei
     h->inflight.push_back(si);
     h->next_slot = (si + 1) % h->depth;
     return MC_OK;
-}
-
-mc_status mc_submit(mc_handle* h, const uint8_t* in, int width, int height, int channels, size_t in_step,
-                    const mc_params* p, uint8_t* out, size_t out_step) try {
-    return submit_impl(h, in, width, height, channels, in_step, p, out, out_step, false);
 } catch (...) { return on_exception(h); }
 
 mc_status mc_collect(mc_handle* h, int* produced) try {
@@ -550,7 +540,7 @@ mc_status mc_process(mc_handle* h, const uint8_t* in, int width, int height, int
     if (!h || !produced) return MC_ERR_INVALID;
     *produced = 0;
     if (!h->inflight.empty()) { h->err = "mc_process called with pipelined frames in flight"; return MC_ERR_INVALID; }
-    mc_status st = submit_impl(h, in, width, height, channels, in_step, p, out, out_step, true);
+    mc_status st = mc_submit(h, in, width, height, channels, in_step, p, out, out_step);
     if (st != MC_OK) return st;
     return mc_collect(h, produced);
 } catch (...) { return on_exception(h); }
